@@ -1,0 +1,836 @@
+// C-ABI implementation (include/himg_cuda.h): context, device scratch, launch sequences.
+// Product code: no CPU fallback and nothing from oracle/ is referenced here.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/himg_cuda.h"
+#include "huff_dec_kernels.cuh"
+#include "huff_enc_kernels.cuh"
+#include "tables.h"
+#include "xform_kernels.cuh"
+
+using namespace himgcu;
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct ProfRec {
+  const char *name;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct himgcu_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::map<std::string, DevBuf> bufs;
+  DevBuf full_lut;  // 7616-byte |x| -> code LUT, uploaded once
+  void *pinned = nullptr;
+  size_t pinned_cap = 0;
+  bool profile = false;
+  std::vector<ProfRec> pending;
+  std::vector<cudaEvent_t> event_pool;
+  std::map<std::string, std::pair<double, int>> prof;
+  std::vector<std::string> prof_names;
+  uint64_t launches = 0;
+  size_t max_workspace = (size_t)24 << 30;
+};
+
+namespace {
+
+int fail(himgcu_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(ctx, HIMGCU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                        \
+  } while (0)
+
+int ensure(himgcu_ctx *ctx, const char *name, size_t bytes, void **out) {
+  DevBuf &b = ctx->bufs[name];
+  if (b.cap < bytes) {
+    if (b.p) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      CK(cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+    }
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+  }
+  *out = b.p;
+  return HIMGCU_OK;
+}
+
+#define ENSURE(name, bytes, ptr)                                             \
+  do {                                                                       \
+    void *p_ = nullptr;                                                      \
+    int rc_ = ensure(ctx, name, (bytes), &p_);                               \
+    if (rc_ != HIMGCU_OK) return rc_;                                        \
+    ptr = reinterpret_cast<decltype(ptr)>(p_);                               \
+  } while (0)
+
+cudaEvent_t get_event(himgcu_ctx *ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct LaunchScope {
+  himgcu_ctx *ctx;
+  const char *name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(himgcu_ctx *c, const char *n) : ctx(c), name(n) {
+    ++ctx->launches;
+    if (ctx->profile) {
+      a = get_event(ctx);
+      b = get_event(ctx);
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (ctx->profile) {
+      cudaEventRecord(b, ctx->stream);
+      ctx->pending.push_back({name, a, b});
+    }
+  }
+};
+
+#define LAUNCH(name, kernel, grid, block, smem, ...)                                         \
+  do {                                                                                       \
+    {                                                                                        \
+      LaunchScope ls_(ctx, name);                                                            \
+      kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__);                               \
+    }                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                     \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(ctx, HIMGCU_ERR_CUDA, "launch %s failed: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+void resolve_profile(himgcu_ctx *ctx) {
+  for (ProfRec &r : ctx->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto it = ctx->prof.find(r.name);
+      if (it == ctx->prof.end()) {
+        ctx->prof[r.name] = {ms, 1};
+        ctx->prof_names.push_back(r.name);
+      } else {
+        it->second.first += ms;
+        it->second.second += 1;
+      }
+    }
+    ctx->event_pool.push_back(r.a);
+    ctx->event_pool.push_back(r.b);
+  }
+  ctx->pending.clear();
+}
+
+Geom make_geom(int w, int h, int nch, int pstride) {
+  Geom g;
+  g.w = w;
+  g.h = h;
+  g.nch = nch;
+  g.pstride = pstride;
+  g.rows = (h + 7) >> 3;
+  g.cols = (w + 7) >> 3;
+  g.mrows = (g.rows + 15) / 16;
+  g.mcols = (g.cols + 15) / 16;
+  g.seg = g.cols * 64 * nch;
+  g.lres_ch = g.mrows * g.mcols + g.rows * g.cols;
+  g.lres_size = g.lres_ch * nch;
+  g.img_bytes = (unsigned long long)w * h * pstride;
+  g.out_img_bytes = (unsigned long long)w * h * nch;
+  g.lres_stride = ((unsigned long long)g.lres_size + 63) & ~63ull;
+  g.planes_bytes = (unsigned long long)g.rows * g.seg;
+  return g;
+}
+
+bool shape_ok(int w, int h, int nch) {
+  if (w < 1 || h < 1 || nch < 1 || nch > 4) return false;
+  const unsigned long long px = (unsigned long long)w * h * nch;
+  return px < (1ull << 31) && ((h + 7) >> 3) <= 65535;
+}
+
+int upload_full_lut(himgcu_ctx *ctx) {
+  if (ctx->full_lut.p) return HIMGCU_OK;
+  CK(cudaMalloc(&ctx->full_lut.p, kFullMapLutSize));
+  ctx->full_lut.cap = kFullMapLutSize;
+  CK(cudaMemcpyAsync(ctx->full_lut.p, FullMapLut(), kFullMapLutSize, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HIMGCU_OK;
+}
+
+QuantParams make_quant(const EncodeTables &t) {
+  QuantParams q;
+  for (int j = 0; j < 64; ++j) {
+    q.shift[0][j] = t.shift_luma[j];
+    q.shift[1][j] = t.shift_chroma[j];
+    q.round[0][j] = t.shift_luma[j] ? 1 << (t.shift_luma[j] - 1) : 0;
+    q.round[1][j] = t.shift_chroma[j] ? 1 << (t.shift_chroma[j] - 1) : 0;
+  }
+  return q;
+}
+
+// ---- stage launchers (device pointers, asynchronous) -------------------------------------------
+
+template <int NCH>
+int launch_avg(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, bool ycbcr, uint8_t *d_avg) {
+  dim3 grid((g.cols + kTile - 1) / kTile, g.rows, n);
+  if (ycbcr) LAUNCH("k_lowres_avg", (k_lowres_avg<NCH, true>), grid, kTile, 0, d_pixels, g, d_avg);
+  else LAUNCH("k_lowres_avg", (k_lowres_avg<NCH, false>), grid, kTile, 0, d_pixels, g, d_avg);
+  return HIMGCU_OK;
+}
+
+int stage_lowres(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, bool ycbcr, uint8_t *d_L) {
+  uint8_t *d_avg;
+  const size_t nlow = (size_t)n * g.nch * g.rows * g.cols;
+  ENSURE("avg", nlow, d_avg);
+  int rc;
+  switch (g.nch) {
+    case 1: rc = launch_avg<1>(ctx, d_pixels, n, g, false, d_avg); break;
+    case 2: rc = launch_avg<2>(ctx, d_pixels, n, g, false, d_avg); break;
+    case 3: rc = launch_avg<3>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
+    default: rc = launch_avg<4>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
+  }
+  if (rc) return rc;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((nlow + threads - 1) / threads);
+  LAUNCH("k_lowres_comp", k_lowres_comp, blocks, threads, 0, d_avg, n * g.nch, g.rows, g.cols, d_L);
+  return HIMGCU_OK;
+}
+
+int upload_lowres_tables(himgcu_ctx *ctx, const EncodeTables *enc, const int16_t *unmap, LowResTables **d_out) {
+  LowResTables h;
+  memset(&h, 0, sizeof(h));
+  if (enc) {
+    memcpy(h.map_lut, enc->low_map_lut, 256);
+    for (int c = 0; c < 128; ++c) h.unmap[c] = (int16_t)enc->low_table[c];
+    for (int k = 1; k <= 127; ++k) h.unmap[256 - k] = (int16_t)(-(int16_t)enc->low_table[k]);
+    h.unmap[128] = h.unmap[129];
+  } else {
+    memcpy(h.unmap, unmap, sizeof(h.unmap));
+  }
+  LowResTables *d;
+  ENSURE("lowres_tables", sizeof(LowResTables), d);
+  CK(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // `h` lives on this stack frame
+  *d_out = d;
+  return HIMGCU_OK;
+}
+
+int stage_lres_encode(himgcu_ctx *ctx, const uint8_t *d_L, int n, const Geom &g, const EncodeTables &t, uint8_t *d_lres) {
+  LowResTables *d_tabs;
+  int rc = upload_lowres_tables(ctx, &t, nullptr, &d_tabs);
+  if (rc) return rc;
+  const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
+  const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
+  LAUNCH("k_lres_dpcm_enc", (k_lres_dpcm<true>), blocks, kLresWarps * 32, 0, d_L, d_lres, (uint8_t *)nullptr, g, n,
+         d_tabs->map_lut, d_tabs->unmap, (unsigned long long)0);
+  return HIMGCU_OK;
+}
+
+template <int NCH>
+int launch_fwd(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
+               const QuantParams &qp, uint8_t *d_planes) {
+  dim3 grid((g.cols + kTile - 1) / kTile, g.rows, n);
+  const uint8_t *lut = (const uint8_t *)ctx->full_lut.p;
+  if (ycbcr) LAUNCH("k_forward", (k_forward<NCH, true>), grid, kTile, 0, d_pixels, d_L, g, qp, lut, d_planes);
+  else LAUNCH("k_forward", (k_forward<NCH, false>), grid, kTile, 0, d_pixels, d_L, g, qp, lut, d_planes);
+  return HIMGCU_OK;
+}
+
+int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g,
+                  const EncodeTables &t, uint8_t *d_planes) {
+  int rc = upload_full_lut(ctx);
+  if (rc) return rc;
+  const QuantParams qp = make_quant(t);
+  switch (g.nch) {
+    case 1: return launch_fwd<1>(ctx, d_pixels, d_L, n, g, false, qp, d_planes);
+    case 2: return launch_fwd<2>(ctx, d_pixels, d_L, n, g, false, qp, d_planes);
+    case 3: return launch_fwd<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, qp, d_planes);
+    default: return launch_fwd<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, qp, d_planes);
+  }
+}
+
+template <int NCH>
+int launch_inv(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
+               const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  dim3 grid((g.cols + kTile - 1) / kTile, g.rows, n);
+  LAUNCH("k_inverse", (k_inverse<NCH>), grid, kTile, 0, d_planes, d_R, g, d_tabs, tab_stride, d_pixels);
+  return HIMGCU_OK;
+}
+
+int stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
+                  const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  switch (g.nch) {
+    case 1: return launch_inv<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    case 2: return launch_inv<2>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    case 3: return launch_inv<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    default: return launch_inv<4>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+  }
+}
+
+// One Huffman chunk per item, or (image mode) LRES + FRES with the container around them.
+struct HuffChunkArgs {
+  const uint8_t *d_in;
+  HuffGeom hg;
+  const char *tag;  // buffer name suffix
+  std::vector<uint8_t> prefix;
+  int size_patch;
+};
+
+int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks, bool riff, uint8_t *d_out,
+                      size_t out_stride, uint32_t *d_sizes) {
+  int *d_err;
+  ENSURE("enc_err", sizeof(int), d_err);
+  CK(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  LayoutParams P;
+  memset(&P, 0, sizeof(P));
+  P.nchunks = nchunks;
+  P.riff_patch = riff ? 1 : 0;
+  P.out = d_out;
+  P.out_stride = out_stride;
+  P.sizes = d_sizes;
+  P.err = d_err;
+  // prefixes of all chunks share one small device buffer
+  size_t prefix_total = 0;
+  for (int k = 0; k < nchunks; ++k) prefix_total += chunks[k].prefix.size();
+  uint8_t *d_prefix = nullptr;
+  if (prefix_total) {
+    ENSURE("enc_prefix", prefix_total, d_prefix);
+    std::vector<uint8_t> all;
+    for (int k = 0; k < nchunks; ++k) all.insert(all.end(), chunks[k].prefix.begin(), chunks[k].prefix.end());
+    CK(cudaMemcpyAsync(d_prefix, all.data(), all.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `all` is a local
+  }
+  size_t prefix_off = 0;
+  TreeOut *d_trees[2];
+  uint32_t *d_seghist[2], *d_bits[2], *d_pos[2];
+  for (int k = 0; k < nchunks; ++k) {
+    const HuffGeom &hg = chunks[k].hg;
+    const std::string tag = chunks[k].tag;
+    ENSURE((tag + "_seghist").c_str(), (size_t)n * hg.nseg * kSyms * sizeof(uint32_t), d_seghist[k]);
+    ENSURE((tag + "_trees").c_str(), (size_t)n * sizeof(TreeOut), d_trees[k]);
+    ENSURE((tag + "_segbits").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_bits[k]);
+    ENSURE((tag + "_segpos").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_pos[k]);
+    dim3 grid(hg.nseg, n);
+    LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
+    LAUNCH("k_huff_tree", k_huff_tree, n, kTreeThreads, 0, d_seghist[k], hg.nseg, d_trees[k], d_err);
+    LayoutChunk &C = P.ch[k];
+    C.seghist = d_seghist[k];
+    C.trees = d_trees[k];
+    C.seg_bits = d_bits[k];
+    C.seg_pos = d_pos[k];
+    C.prefix = chunks[k].prefix.empty() ? nullptr : d_prefix + prefix_off;
+    C.prefix_len = (int)chunks[k].prefix.size();
+    C.size_patch = chunks[k].size_patch;
+    C.nseg = hg.nseg;
+    C.framed = hg.nseg > 1 ? 1 : 0;
+    prefix_off += chunks[k].prefix.size();
+  }
+  LAUNCH("k_huff_layout", k_huff_layout, n, kLayoutThreads, 0, P);
+  const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_huff_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
+    attr_set = true;
+  }
+  for (int k = 0; k < nchunks; ++k) {
+    const HuffGeom &hg = chunks[k].hg;
+    dim3 grid(hg.nseg, n);
+    LAUNCH("k_huff_pack", k_huff_pack, grid, kHuffThreads, win_bytes, chunks[k].d_in, hg, d_trees[k], d_bits[k],
+           d_pos[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
+    if (hg.nseg > 1) {
+      const long long tot = (long long)n * hg.nseg;
+      LAUNCH("k_huff_stale", k_huff_stale, (unsigned)((tot + 255) / 256), 256, 0, n, hg.nseg, d_bits[k], d_pos[k],
+             d_sizes, d_out, (unsigned long long)out_stride);
+    }
+  }
+  return HIMGCU_OK;
+}
+
+int read_err_flag(himgcu_ctx *ctx, const char *name, int *value) {
+  int *d_err;
+  ENSURE(name, sizeof(int), d_err);
+  CK(cudaMemcpyAsync(value, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HIMGCU_OK;
+}
+
+size_t per_image_encode_ws(const Geom &g) {
+  return 2 * (size_t)g.nch * g.rows * g.cols + g.lres_stride + g.planes_bytes +
+         (size_t)(g.rows + 1) * kSyms * 4 + 2 * sizeof(TreeOut) + (size_t)(g.rows + 1) * 8;
+}
+
+// Whole-image encode of a sub-batch already resident on the device.
+int encode_device(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, int quality, bool ycbcr,
+                  uint8_t *d_out, size_t out_stride, uint32_t *d_sizes) {
+  EncodeTables t;
+  BuildEncodeTables(quality, ycbcr, &t);
+  ContainerTemplate ct;
+  BuildContainerTemplate(t, g.w, g.h, g.nch, &ct);
+  uint8_t *d_L, *d_lres, *d_planes;
+  ENSURE("L", (size_t)n * g.nch * g.rows * g.cols, d_L);
+  ENSURE("lres", (size_t)n * g.lres_stride, d_lres);
+  ENSURE("planes", (size_t)n * g.planes_bytes, d_planes);
+  int rc = stage_lowres(ctx, d_pixels, n, g, ycbcr, d_L);
+  if (rc) return rc;
+  rc = stage_lres_encode(ctx, d_L, n, g, t, d_lres);
+  if (rc) return rc;
+  rc = stage_forward(ctx, d_pixels, d_L, n, g, t, d_planes);
+  if (rc) return rc;
+  HuffChunkArgs ch[2];
+  ch[0].d_in = d_lres;
+  ch[0].hg = HuffGeom{g.lres_size, g.lres_size, 1, g.lres_stride};
+  ch[0].tag = "lres";
+  ch[0].prefix = ct.head;
+  ch[0].size_patch = (int)ct.head.size() - 4;
+  ch[1].d_in = d_planes;
+  ch[1].hg = HuffGeom{(int)g.planes_bytes, g.seg, g.rows, g.planes_bytes};
+  ch[1].tag = "fres";
+  ch[1].prefix = ct.mid;
+  ch[1].size_patch = (int)ct.mid.size() - 4;
+  return huff_encode_items(ctx, n, ch, 2, true, d_out, out_stride, d_sizes);
+}
+
+// Whole-image decode of n streams resident on the device.
+int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long long *d_offsets,
+                  const uint32_t *d_sizes, int n, const Geom &g, int flags, uint8_t *d_pixels, int *d_status) {
+  const int lenient = (flags & HIMGCU_LENIENT) ? 1 : 0;
+  ChunkDesc *d_lcd, *d_fcd;
+  DecTables *d_tabs;
+  DecTree *d_ltree, *d_ftree;
+  SegRef *d_lseg, *d_fseg;
+  uint8_t *d_lres, *d_planes, *d_R;
+  ENSURE("dec_lcd", (size_t)n * sizeof(ChunkDesc), d_lcd);
+  ENSURE("dec_fcd", (size_t)n * sizeof(ChunkDesc), d_fcd);
+  ENSURE("dec_tabs", (size_t)n * sizeof(DecTables), d_tabs);
+  ENSURE("dec_ltree", (size_t)n * sizeof(DecTree), d_ltree);
+  ENSURE("dec_ftree", (size_t)n * sizeof(DecTree), d_ftree);
+  ENSURE("dec_lseg", (size_t)n * sizeof(SegRef), d_lseg);
+  ENSURE("dec_fseg", (size_t)n * g.rows * sizeof(SegRef), d_fseg);
+  ENSURE("lres", (size_t)n * g.lres_stride, d_lres);
+  ENSURE("planes", (size_t)n * g.planes_bytes, d_planes);
+  ENSURE("L", (size_t)n * g.nch * g.rows * g.cols, d_R);
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  LAUNCH("k_dec_parse", k_dec_parse, nb, 128, 0, d_himg, d_offsets, d_sizes, n, g.w, g.h, g.nch, d_lcd, d_fcd,
+         d_tabs, d_status);
+  LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_himg, d_lcd, lenient, d_ltree, d_status);
+  LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_himg, d_fcd, lenient, d_ftree, d_status);
+  LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_lcd, d_ltree, n, 1, g.lres_size, 0, lenient, d_lseg,
+         d_status);
+  LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
+         d_status);
+  LAUNCH("k_dec_stream_lres", k_dec_stream, dim3(1, n), kDecThreads, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
+         g.lres_size, d_lres, g.lres_stride, d_status);
+  LAUNCH("k_dec_stream_fres", k_dec_stream, dim3((g.rows + kDecThreads - 1) / kDecThreads, n), kDecThreads, 0,
+         d_himg, d_fcd, d_ftree, d_fseg, g.rows, g.seg, d_planes, g.planes_bytes, d_status);
+  const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
+  const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
+  LAUNCH("k_lres_dpcm_dec", (k_lres_dpcm<false>), blocks, kLresWarps * 32, 0, (const uint8_t *)nullptr, d_lres, d_R,
+         g, n, (const uint8_t *)nullptr, d_tabs->low_unmap, (unsigned long long)sizeof(DecTables));
+  return stage_inverse(ctx, d_planes, d_R, n, g, d_tabs, sizeof(DecTables), d_pixels);
+}
+
+int ensure_pinned(himgcu_ctx *ctx, size_t bytes) {
+  if (ctx->pinned_cap >= bytes) return HIMGCU_OK;
+  if (ctx->pinned) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFreeHost(ctx->pinned));
+    ctx->pinned = nullptr;
+    ctx->pinned_cap = 0;
+  }
+  CK(cudaMallocHost(&ctx->pinned, bytes));
+  ctx->pinned_cap = bytes;
+  return HIMGCU_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int himgcu_abi_version(void) { return 1; }
+
+int himgcu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int himgcu_create(int device, himgcu_ctx **out) {
+  if (!out) return HIMGCU_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return HIMGCU_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return HIMGCU_ERR_CUDA;
+  himgcu_ctx *ctx = new himgcu_ctx();
+  ctx->device = device;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return HIMGCU_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return HIMGCU_OK;
+}
+
+void himgcu_destroy(himgcu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  resolve_profile(ctx);
+  for (auto &kv : ctx->bufs)
+    if (kv.second.p) cudaFree(kv.second.p);
+  if (ctx->full_lut.p) cudaFree(ctx->full_lut.p);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int himgcu_set_stream(himgcu_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return HIMGCU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return HIMGCU_OK;
+}
+
+int himgcu_reset_stream(himgcu_ctx *ctx) {
+  if (!ctx) return HIMGCU_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = ctx->own_stream;
+  return HIMGCU_OK;
+}
+
+int himgcu_synchronize(himgcu_ctx *ctx) {
+  if (!ctx) return HIMGCU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  resolve_profile(ctx);
+  return HIMGCU_OK;
+}
+
+const char *himgcu_last_error(himgcu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+size_t himgcu_encode_bound(int w, int h, int nch) {
+  if (!shape_ok(w, h, nch)) return 0;
+  const Geom g = make_geom(w, h, nch, nch);
+  // RIFF(12) FRMT(19) LMAP(136) LRES hdr(8) QCFG(72) FMAP(188) FRES hdr(8) + two Huffman chunks with
+  // the reference's own head-room (MaxCompressedSize = n + 359, huffman_enc.cpp:242-244) plus the
+  // per-segment size headers.
+  return 12 + 19 + 136 + 8 + 72 + 188 + 8 + (size_t)g.lres_size + 359 + (size_t)g.planes_bytes + 359 +
+         (size_t)4 * g.rows + 64;
+}
+
+size_t himgcu_lres_size(int w, int h, int nch) { return shape_ok(w, h, nch) ? (size_t)make_geom(w, h, nch, nch).lres_size : 0; }
+size_t himgcu_lres_stride(int w, int h, int nch) { return shape_ok(w, h, nch) ? (size_t)make_geom(w, h, nch, nch).lres_stride : 0; }
+
+int himgcu_encode_batch(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, int w, int h, int nch, int quality,
+                        int use_ycbcr, uint8_t *d_out, size_t out_stride, uint32_t *d_sizes) {
+  if (!ctx || !d_pixels || !d_out || !d_sizes || n < 0) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  if (!shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", w, h, nch);
+  if (n == 0) return HIMGCU_OK;
+  CK(cudaSetDevice(ctx->device));
+  const Geom g = make_geom(w, h, nch, nch);
+  const bool ycbcr = use_ycbcr && nch >= 3;
+  const size_t per = per_image_encode_ws(g);
+  int sub = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, ctx->max_workspace / per));
+  sub = std::min(sub, 65535);
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int m = std::min(sub, n - i0);
+    int rc = encode_device(ctx, d_pixels + (size_t)i0 * g.img_bytes, m, g, quality, ycbcr,
+                           d_out + (size_t)i0 * out_stride, out_stride, d_sizes + i0);
+    if (rc) return rc;
+  }
+  return HIMGCU_OK;
+}
+
+int himgcu_encode(himgcu_ctx *ctx, const uint8_t *pixels, int w, int h, int pixel_stride, int nch, int quality,
+                  int use_ycbcr, uint8_t *out, size_t out_cap, size_t *out_size) {
+  if (!ctx || !pixels || !out || !out_size) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  if (!shape_ok(w, h, nch) || pixel_stride < nch || pixel_stride > 64)
+    return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d stride %d", w, h, nch, pixel_stride);
+  CK(cudaSetDevice(ctx->device));
+  *out_size = 0;
+  const Geom g = make_geom(w, h, nch, pixel_stride);
+  const bool ycbcr = use_ycbcr && nch >= 3;
+  const size_t bound = himgcu_encode_bound(w, h, nch);
+  uint8_t *d_in, *d_out;
+  uint32_t *d_size;
+  ENSURE("single_in", g.img_bytes, d_in);
+  ENSURE("single_out", bound, d_out);
+  ENSURE("single_size", sizeof(uint32_t), d_size);
+  CK(cudaMemcpyAsync(d_in, pixels, g.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = encode_device(ctx, d_in, 1, g, quality, ycbcr, d_out, bound, d_size);
+  if (rc) return rc;
+  uint32_t size = 0;
+  CK(cudaMemcpyAsync(&size, d_size, sizeof(size), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int err = 0;
+  rc = read_err_flag(ctx, "enc_err", &err);
+  if (rc) return rc;
+  if (err == 5) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "Huffman code longer than 32 bits");
+  if (err == 99) return fail(ctx, HIMGCU_ERR_CUDA, "internal: packed size mismatch");
+  if (size == 0 || err) return fail(ctx, HIMGCU_ERR_CAPACITY, "internal output bound exceeded");
+  if (size > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small: need %u", size);
+  CK(cudaMemcpyAsync(out, d_out, size, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out_size = size;
+  return HIMGCU_OK;
+}
+
+int himgcu_decode_info(const uint8_t *p, size_t size, int *w, int *h, int *nch) {
+  if (!p || size < 12 || memcmp(p, "RIFF", 4) || memcmp(p + 8, "HIMG", 4)) return HIMGCU_REJECT;
+  auto u32 = [&](size_t o) { return (uint32_t)p[o] | ((uint32_t)p[o + 1] << 8) | ((uint32_t)p[o + 2] << 16) | ((uint32_t)p[o + 3] << 24); };
+  if ((long long)(int)u32(4) + 8 != (long long)size) return HIMGCU_REJECT;
+  size_t idx = 12;
+  for (;;) {
+    if (idx + 8 > size) return HIMGCU_REJECT;
+    const uint32_t cc = u32(idx);
+    const int sz = (int)u32(idx + 4);
+    idx += 8;
+    if (sz < 0 || idx + (size_t)sz > size) return HIMGCU_REJECT;
+    if (cc == 0x544d5246u) {
+      if (sz < 11 || p[idx] != 1) return HIMGCU_REJECT;
+      if (w) *w = (int)u32(idx + 1);
+      if (h) *h = (int)u32(idx + 5);
+      if (nch) *nch = p[idx + 9];
+      return HIMGCU_OK;
+    }
+    idx += sz;
+  }
+}
+
+int himgcu_decode_batch(himgcu_ctx *ctx, const uint8_t *d_himg, const uint64_t *d_offsets, const uint32_t *d_sizes,
+                        int n, int w, int h, int nch, int flags, uint8_t *d_pixels_out, int32_t *d_status) {
+  if (!ctx || !d_himg || !d_offsets || !d_sizes || !d_pixels_out || !d_status || n < 0)
+    return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  if (!shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", w, h, nch);
+  if (n == 0) return HIMGCU_OK;
+  CK(cudaSetDevice(ctx->device));
+  const Geom g = make_geom(w, h, nch, nch);
+  const size_t per = per_image_encode_ws(g) + sizeof(DecTables) + 2 * sizeof(DecTree);
+  int sub = (int)std::min<size_t>((size_t)n, std::max<size_t>(1, ctx->max_workspace / per));
+  sub = std::min(sub, 65535);
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int m = std::min(sub, n - i0);
+    int rc = decode_device(ctx, d_himg, reinterpret_cast<const unsigned long long *>(d_offsets) + i0, d_sizes + i0, m,
+                           g, flags, d_pixels_out + (size_t)i0 * g.out_img_bytes, d_status + i0);
+    if (rc) return rc;
+  }
+  return HIMGCU_OK;
+}
+
+int himgcu_decode(himgcu_ctx *ctx, const uint8_t *himg, size_t size, int flags, uint8_t *out, size_t out_cap, int *w,
+                  int *h, int *nch) {
+  if (!ctx || !himg || !out) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  int W = 0, H = 0, N = 0;
+  if (himgcu_decode_info(himg, size, &W, &H, &N) != HIMGCU_OK) return fail(ctx, HIMGCU_REJECT, "not a HIMG stream");
+  if (w) *w = W;
+  if (h) *h = H;
+  if (nch) *nch = N;
+  if (W < 1 || H < 1 || N < 1) return fail(ctx, HIMGCU_REJECT, "bad dimensions");
+  if (!shape_ok(W, H, N)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", W, H, N);
+  if (size > 0xffffffffull) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "stream too large");
+  CK(cudaSetDevice(ctx->device));
+  const Geom g = make_geom(W, H, N, N);
+  if (g.out_img_bytes > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small");
+  uint8_t *d_in, *d_px;
+  unsigned long long *d_off;
+  uint32_t *d_sz;
+  int *d_status;
+  ENSURE("single_in", size + 16, d_in);
+  ENSURE("single_px", g.out_img_bytes, d_px);
+  ENSURE("single_off", sizeof(unsigned long long), d_off);
+  ENSURE("single_size", sizeof(uint32_t), d_sz);
+  ENSURE("single_status", sizeof(int), d_status);
+  const unsigned long long zero = 0;
+  const uint32_t sz32 = (uint32_t)size;
+  CK(cudaMemcpyAsync(d_in, himg, size, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_off, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_sz, &sz32, sizeof(sz32), cudaMemcpyHostToDevice, ctx->stream));
+  int rc = decode_device(ctx, d_in, d_off, d_sz, 1, g, flags, d_px, d_status);
+  if (rc) return rc;
+  int status = 0;
+  CK(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (status) return fail(ctx, HIMGCU_REJECT, "stream rejected");
+  CK(cudaMemcpyAsync(out, d_px, g.out_img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HIMGCU_OK;
+}
+
+// ---- stage-level entry points ------------------------------------------------------------------
+
+int himgcu_stage_lowres(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, int w, int h, int pixel_stride, int nch,
+                        int use_ycbcr, uint8_t *d_L) {
+  if (!ctx || !d_pixels || !d_L || n < 1 || !shape_ok(w, h, nch) || pixel_stride < nch) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  return stage_lowres(ctx, d_pixels, n, make_geom(w, h, nch, pixel_stride), use_ycbcr && nch >= 3, d_L);
+}
+
+int himgcu_stage_lres_encode(himgcu_ctx *ctx, const uint8_t *d_L, int n, int w, int h, int nch, int quality,
+                             uint8_t *d_lres) {
+  if (!ctx || !d_L || !d_lres || n < 1 || !shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  EncodeTables t;
+  BuildEncodeTables(quality, false, &t);
+  return stage_lres_encode(ctx, d_L, n, make_geom(w, h, nch, nch), t, d_lres);
+}
+
+int himgcu_stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, int w, int h,
+                         int pixel_stride, int nch, int quality, int use_ycbcr, uint8_t *d_planes) {
+  if (!ctx || !d_pixels || !d_L || !d_planes || n < 1 || !shape_ok(w, h, nch) || pixel_stride < nch)
+    return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  EncodeTables t;
+  BuildEncodeTables(quality, use_ycbcr && nch >= 3, &t);
+  return stage_forward(ctx, d_pixels, d_L, n, make_geom(w, h, nch, pixel_stride), t, d_planes);
+}
+
+int himgcu_stage_huff_compress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in_stride, int n, int in_size,
+                               int block_size, uint8_t *d_out, size_t out_stride, uint32_t *d_sizes) {
+  if (!ctx || !d_in || !d_out || !d_sizes || n < 1 || in_size < 1) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  if (block_size < 1) block_size = in_size;
+  if (in_size % block_size) return fail(ctx, HIMGCU_ERR_ARG, "in_size is not a multiple of block_size");
+  if (in_size / block_size > 65535) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "too many segments");
+  CK(cudaSetDevice(ctx->device));
+  HuffChunkArgs ch;
+  ch.d_in = d_in;
+  ch.hg = HuffGeom{in_size, block_size, in_size / block_size, (unsigned long long)in_stride};
+  ch.tag = "stage";
+  ch.size_patch = -1;
+  return huff_encode_items(ctx, n, &ch, 1, false, d_out, out_stride, d_sizes);
+}
+
+int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in_stride, const uint32_t *d_in_sizes,
+                                 int n, int out_size, int block_size, int flags, uint8_t *d_out, size_t out_stride,
+                                 int32_t *d_status) {
+  if (!ctx || !d_in || !d_in_sizes || !d_out || !d_status || n < 1 || out_size < 1) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  const int lenient = (flags & HIMGCU_LENIENT) ? 1 : 0;
+  const bool whole = block_size < 1;  // Uncompress() vs UncompressBlock()
+  const int seg = whole ? out_size : block_size;
+  if (out_size % seg || (seg & 3)) return fail(ctx, HIMGCU_ERR_ARG, "segment size must divide out_size and be a multiple of 4");
+  if (out_stride & 3) return fail(ctx, HIMGCU_ERR_ARG, "out_stride must be a multiple of 4");
+  const int nseg = out_size / seg;
+  CK(cudaSetDevice(ctx->device));
+  ChunkDesc *d_cd;
+  DecTree *d_tree;
+  SegRef *d_seg;
+  ENSURE("stage_cd", (size_t)n * sizeof(ChunkDesc), d_cd);
+  ENSURE("stage_dtree", (size_t)n * sizeof(DecTree), d_tree);
+  ENSURE("stage_dseg", (size_t)n * nseg * sizeof(SegRef), d_seg);
+  const unsigned nb = (unsigned)((n + 127) / 128);
+  LAUNCH("k_dec_make_desc", k_dec_make_desc, nb, 128, 0, (unsigned long long)in_stride, d_in_sizes, n, d_cd, d_status);
+  LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_in, d_cd, lenient, d_tree, d_status);
+  LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_in, d_cd, d_tree, n, nseg, seg, whole ? 0 : 1, lenient, d_seg,
+         d_status);
+  LAUNCH("k_dec_stream", k_dec_stream, dim3((nseg + kDecThreads - 1) / kDecThreads, n), kDecThreads, 0, d_in, d_cd,
+         d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);
+  return HIMGCU_OK;
+}
+
+int himgcu_stage_lres_decode(himgcu_ctx *ctx, const uint8_t *d_lres, size_t lres_stride, int n, int w, int h, int nch,
+                             const int16_t *unmap, uint8_t *d_R) {
+  if (!ctx || !d_lres || !unmap || !d_R || n < 1 || !shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  Geom g = make_geom(w, h, nch, nch);
+  g.lres_stride = lres_stride;
+  LowResTables *d_tabs;
+  int rc = upload_lowres_tables(ctx, nullptr, unmap, &d_tabs);
+  if (rc) return rc;
+  const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
+  const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
+  LAUNCH("k_lres_dpcm_dec", (k_lres_dpcm<false>), blocks, kLresWarps * 32, 0, (const uint8_t *)nullptr,
+         const_cast<uint8_t *>(d_lres), d_R, g, n, (const uint8_t *)nullptr, d_tabs->unmap, (unsigned long long)0);
+  return HIMGCU_OK;
+}
+
+int himgcu_stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, int w, int h, int nch,
+                         int use_ycbcr, const uint8_t *shift_luma, const uint8_t *shift_chroma, const int16_t *unmap,
+                         uint8_t *d_pixels) {
+  if (!ctx || !d_planes || !d_R || !shift_luma || !shift_chroma || !unmap || !d_pixels || n < 1 || !shape_ok(w, h, nch))
+    return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(ctx->device));
+  DecTables t;
+  memset(&t, 0, sizeof(t));
+  memcpy(t.full_unmap, unmap, sizeof(t.full_unmap));
+  memcpy(t.shift[0], shift_luma, 64);
+  memcpy(t.shift[1], shift_chroma, 64);
+  t.ycbcr = (use_ycbcr && nch >= 3) ? 1 : 0;
+  DecTables *d_t;
+  ENSURE("stage_dectabs", sizeof(DecTables), d_t);
+  CK(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return stage_inverse(ctx, d_planes, d_R, n, make_geom(w, h, nch, nch), d_t, 0, d_pixels);
+}
+
+// ---- profiling ---------------------------------------------------------------------------------
+
+int himgcu_profile_enable(himgcu_ctx *ctx, int on) {
+  if (!ctx) return HIMGCU_ERR_ARG;
+  ctx->profile = on != 0;
+  return HIMGCU_OK;
+}
+
+int himgcu_profile_reset(himgcu_ctx *ctx) {
+  if (!ctx) return HIMGCU_ERR_ARG;
+  cudaStreamSynchronize(ctx->stream);
+  resolve_profile(ctx);
+  ctx->prof.clear();
+  ctx->prof_names.clear();
+  return HIMGCU_OK;
+}
+
+int himgcu_profile_count(himgcu_ctx *ctx) {
+  if (!ctx) return 0;
+  cudaStreamSynchronize(ctx->stream);
+  resolve_profile(ctx);
+  return (int)ctx->prof_names.size();
+}
+
+int himgcu_profile_get(himgcu_ctx *ctx, int index, const char **name, double *total_ms, int *launches) {
+  if (!ctx || index < 0 || index >= (int)ctx->prof_names.size()) return HIMGCU_ERR_ARG;
+  const std::string &k = ctx->prof_names[index];
+  if (name) *name = k.c_str();
+  if (total_ms) *total_ms = ctx->prof[k].first;
+  if (launches) *launches = ctx->prof[k].second;
+  return HIMGCU_OK;
+}
+
+uint64_t himgcu_launch_count(himgcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

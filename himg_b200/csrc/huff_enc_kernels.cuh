@@ -1,0 +1,633 @@
+// RLE + Huffman ENCODE kernels (reference: huffman_enc.cpp:98-363).
+//
+//   k_huff_hist    block-parallel zero-run tokenisation + 261-bin histogram per segment
+//   k_huff_tree    one CTA per chunk: histogram total -> Huffman tree with the reference's exact
+//                  tie-breaking -> (code,len) table + serialised tree
+//   k_huff_layout  per item: segment bit lengths (histogram . code length), prefix sum of
+//                  (header + payload) sizes -> absolute byte offsets; writes container headers
+//   k_huff_pack    CTA per segment: token bit lengths -> scan -> thread-local bit accumulation
+//                  into a shared-memory bit window -> bytes to the final position
+//   k_huff_stale   the reference's uncleared scratch buffer leaks "stale" bits into the padding of
+//                  every segment's last byte; reproduced as a fix-up pass
+//
+// Tokenisation is "emit at run end": a thread owns the tokens that END inside its 32-byte chunk,
+// so it only needs the number of zeros immediately preceding the chunk (one forward scan), and
+// tokens stay in stream order.
+#ifndef HIMG_B200_HUFF_ENC_KERNELS_CUH_
+#define HIMG_B200_HUFF_ENC_KERNELS_CUH_
+
+#include "common.cuh"
+
+namespace himgcu {
+
+constexpr int kHuffThreads = 512;
+constexpr int kChunkBytes = 32;
+constexpr int kPieceBytes = kHuffThreads * kChunkBytes;  // 16 KiB per CTA iteration
+constexpr int kWinWords = 8192;                          // bit window: 32 KiB + 2 words of slack
+constexpr int kWinBits = kWinWords * 32;
+
+struct HuffGeom {
+  int in_size;   // unpacked bytes per chunk
+  int seg_size;  // bytes per segment (== in_size when the chunk is unframed)
+  int nseg;
+  unsigned long long in_stride;  // bytes between the chunks of consecutive items
+};
+
+struct TreeOut {
+  uint32_t code[kSyms];
+  uint32_t hist[kSyms];
+  uint8_t len[kSyms + 3];
+  uint8_t tree[kTreeBytesMax];
+  uint32_t tree_bits;
+  uint32_t nleaves;
+};
+
+__device__ __forceinline__ int sym_extra_bits(int s) {
+  return s < 257 ? 0 : (s == 257 ? 2 : (s == 258 ? 4 : (s == 259 ? 8 : 14)));
+}
+
+// ---- per-thread chunk of a segment ---------------------------------------------------------
+struct Chunk {
+  uint32_t w[8];
+  int valid;  // number of valid bytes (0..32)
+};
+
+__device__ __forceinline__ void load_chunk(Chunk &c, const uint8_t *__restrict__ seg, int seg_size, int off) {
+  c.valid = min(max(seg_size - off, 0), kChunkBytes);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c.w[k] = 0;
+  if (c.valid == kChunkBytes && ((reinterpret_cast<uintptr_t>(seg + off)) & 15) == 0) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(seg + off));
+    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(seg + off) + 1);
+    c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
+    c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kChunkBytes; ++k)
+      if (k < c.valid) c.w[k >> 2] |= (uint32_t)seg[off + k] << (8 * (k & 3));
+  }
+}
+
+// Zero-run summary of a chunk: low 31 bits = trailing zeros, bit 31 = "all zero" (an empty chunk
+// is the identity).  combine(X earlier, Y later) is associative.
+__device__ __forceinline__ uint32_t run_summary(const Chunk &c) {
+  if (c.valid == 0) return 0x80000000u;
+  int tz = 0;
+  bool all = true;
+#pragma unroll
+  for (int k = kChunkBytes - 1; k >= 0; --k) {
+    if (k < c.valid && all) {
+      if (((c.w[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0) ++tz;
+      else all = false;
+    }
+  }
+  return (uint32_t)tz | (all ? 0x80000000u : 0u);
+}
+__device__ __forceinline__ uint32_t run_combine(uint32_t x, uint32_t y) {
+  return (y & 0x80000000u) ? (((x & 0x7fffffffu) + (y & 0x7fffffffu)) | (x & 0x80000000u)) : y;
+}
+
+// Exclusive scan of run summaries over the block, seeded with the zeros carried in from earlier
+// pieces.  Returns the number of zeros immediately preceding this thread's chunk; *carry_out is
+// the trailing-zero count after the whole piece.  `ws` needs 17 words.
+__device__ __forceinline__ uint32_t block_run_scan(uint32_t mine, uint32_t carry_in, uint32_t *ws, uint32_t *carry_out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc = run_combine(t, inc);
+  }
+  __syncthreads();
+  if (lane == 31) ws[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = lane < nw ? ws[lane] : 0x80000000u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s = run_combine(t, s);
+    }
+    if (lane < nw) ws[lane] = s;
+  }
+  __syncthreads();
+  uint32_t prev = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) prev = 0x80000000u;  // identity
+  uint32_t ex = wid ? run_combine(ws[wid - 1], prev) : prev;
+  const uint32_t seed = carry_in | 0x80000000u;
+  ex = run_combine(seed, ex);
+  *carry_out = run_combine(seed, ws[nw - 1]) & 0x7fffffffu;
+  return ex & 0x7fffffffu;
+}
+
+// ---- token walk ------------------------------------------------------------------------------
+template <class Sink>
+__device__ __forceinline__ void emit_run(uint32_t z, Sink &s) {
+  while (z >= (uint32_t)kMaxRun) {  // runs are cut greedily from their start (huffman_enc.cpp:111)
+    s.tok(260, kMaxRun - 279, 14);
+    z -= kMaxRun;
+  }
+  if (z == 0) return;
+  if (z == 1) s.tok(0, 0, 0);
+  else if (z == 2) s.tok(256, 0, 0);
+  else if (z <= 6) s.tok(257, z - 3, 2);
+  else if (z <= 22) s.tok(258, z - 7, 4);
+  else if (z <= 278) s.tok(259, z - 23, 8);
+  else s.tok(260, z - 279, 14);
+}
+
+// z_in: zeros immediately before the chunk; flush_end: the chunk holds the segment's last byte.
+template <class Sink>
+__device__ __forceinline__ void walk_chunk(const Chunk &c, uint32_t z_in, bool flush_end, Sink &s) {
+  uint32_t z = z_in;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (4 * k < c.valid) {
+      const uint32_t word = c.w[k];
+      if (word == 0 && 4 * k + 4 <= c.valid) {
+        z += 4;
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (4 * k + b < c.valid) {
+            const uint32_t byte = (word >> (8 * b)) & 0xffu;
+            if (byte == 0) {
+              ++z;
+            } else {
+              if (z) {
+                emit_run(z, s);
+                z = 0;
+              }
+              s.tok((int)byte, 0, 0);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (flush_end && z) emit_run(z, s);
+}
+
+// ---- K-hist ----------------------------------------------------------------------------------
+struct HistSink {
+  uint32_t *h;
+  __device__ __forceinline__ void tok(int sym, uint32_t, int) { atomicAdd(&h[sym], 1u); }
+};
+
+// grid (nseg, n).  seghist: [n][nseg][261].
+__global__ void __launch_bounds__(kHuffThreads)
+    k_huff_hist(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist) {
+  __shared__ uint32_t sh[kSyms];
+  __shared__ uint32_t ws[17];
+  for (int i = threadIdx.x; i < kSyms; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint8_t *seg = in + (size_t)blockIdx.y * hg.in_stride + (size_t)blockIdx.x * hg.seg_size;
+  uint32_t carry = 0;
+  HistSink sink{sh};
+  for (int base = 0; base < hg.seg_size; base += kPieceBytes) {
+    const int off = base + threadIdx.x * kChunkBytes;
+    Chunk c;
+    load_chunk(c, seg, hg.seg_size, off);
+    uint32_t carry_out;
+    const uint32_t z_in = block_run_scan(run_summary(c), carry, ws, &carry_out);
+    carry = carry_out;
+    walk_chunk(c, z_in, c.valid > 0 && off + c.valid == hg.seg_size, sink);
+  }
+  __syncthreads();
+  uint32_t *dst = seghist + ((size_t)blockIdx.y * hg.nseg + blockIdx.x) * kSyms;
+  for (int i = threadIdx.x; i < kSyms; i += blockDim.x) dst[i] = sh[i];
+}
+
+// ---- K-tree ----------------------------------------------------------------------------------
+constexpr int kTreeThreads = 288;
+
+// grid (n).  err: set to HIMGCU_ERR_UNSUPPORTED (5) if a code exceeds 32 bits.
+__global__ void __launch_bounds__(kTreeThreads)
+    k_huff_tree(const uint32_t *__restrict__ seghist, int nseg, TreeOut *__restrict__ trees, int *err) {
+  __shared__ uint32_t cnt[kMaxNodes];
+  __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
+  __shared__ short lq[kSyms];
+  __shared__ short ist[kSyms], g_start[kSyms], g_top[kSyms];
+  __shared__ uint32_t g_count[kSyms];
+  __shared__ uint32_t s_code[kSyms];
+  __shared__ uint8_t s_len[kSyms + 3];
+  __shared__ uint32_t s_tree[kTreeBytesMax / 4];
+  __shared__ uint32_t warp_tot[kTreeThreads / 32 + 1];
+  __shared__ int s_nleaves, s_root, s_bits;
+  __shared__ short st_node[kSyms + 1];
+  __shared__ uint8_t st_bits[kSyms + 1];
+  __shared__ uint32_t st_code[kSyms + 1];
+
+  const int t = threadIdx.x;
+  TreeOut *out = trees + blockIdx.x;
+  // 1. chunk histogram = sum of its segments' histograms (coalesced across threads)
+  uint32_t my = 0;
+  if (t < kSyms) {
+    const uint32_t *p = seghist + (size_t)blockIdx.x * nseg * kSyms + t;
+    for (int s = 0; s < nseg; ++s) my += p[(size_t)s * kSyms];
+    out->hist[t] = my;
+    s_code[t] = 0;
+    s_len[t] = 0;
+  }
+  for (int i = t; i < kTreeBytesMax / 4; i += blockDim.x) s_tree[i] = 0;
+  // 2. leaves = used symbols in symbol order (huffman_enc.cpp:186-196)
+  uint32_t total;
+  const uint32_t li = block_exscan_u32(t < kSyms && my ? 1u : 0u, warp_tot, &total);
+  if (t < kSyms && my) {
+    cnt[li] = my;
+    ca[li] = cb[li] = -1;
+    nsym[li] = (short)t;
+  }
+  if (t == 0) s_nleaves = (int)total;
+  __syncthreads();
+  const int n = s_nleaves;
+  // 3. rank sort under (count ascending, index DEscending): keys are unique
+  if (t < n) {
+    const uint32_t c = cnt[t];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const uint32_t cj = cnt[j];
+      rank += (cj < c || (cj == c && j > t)) ? 1 : 0;
+    }
+    lq[rank] = (short)t;
+  }
+  __syncthreads();
+  if (t == 0) {
+    // 4. two-queue merge.  Internal nodes are created with non-decreasing counts; equal-count
+    //    internal nodes form groups consumed front group first, NEWEST first inside a group, and
+    //    an internal node beats a leaf of equal count (the reference picks the minimum under
+    //    (count asc, node index desc); huffman_enc.cpp:199-227).
+    int root = 0;
+    if (n > 1) {
+      int ist_n = 0, gfront = 0, glast = -1, lp = 0, next = n;
+      for (int merge = 0; merge < n - 1; ++merge) {
+        int pick[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          while (gfront < glast && g_top[gfront] == g_start[gfront]) ++gfront;
+          const bool have_int = glast >= 0 && gfront <= glast &&
+                                (gfront == glast ? ist_n > g_start[glast] : g_top[gfront] > g_start[gfront]);
+          const bool take_int = have_int && (lp >= n || g_count[gfront] <= cnt[lq[lp]]);
+          if (take_int) pick[k] = (gfront == glast) ? ist[--ist_n] : ist[--g_top[gfront]];
+          else pick[k] = lq[lp++];
+        }
+        root = next++;
+        ca[root] = (short)pick[0];
+        cb[root] = (short)pick[1];
+        nsym[root] = -1;
+        const uint32_t c = cnt[pick[0]] + cnt[pick[1]];
+        cnt[root] = c;
+        if (glast >= 0 && ist_n > g_start[glast] && g_count[glast] == c) {
+          ist[ist_n++] = (short)root;
+        } else if (glast >= 0 && ist_n == g_start[glast]) {
+          g_count[glast] = c;
+          ist[ist_n++] = (short)root;
+        } else {
+          if (glast >= 0) g_top[glast] = (short)ist_n;
+          ++glast;
+          g_start[glast] = (short)ist_n;
+          g_count[glast] = c;
+          ist[ist_n++] = (short)root;
+        }
+      }
+    }
+    s_root = root;
+    // 5. pre-order serialisation + code assignment (huffman_enc.cpp:148-180, :229-237)
+    int nbits = 0;
+    if (n > 0) {
+      int sp = 0;
+      st_node[0] = (short)root;
+      st_bits[0] = n == 1 ? 1 : 0;
+      st_code[0] = 0;
+      sp = 1;
+      uint64_t acc = 0;
+      int nacc = 0, wpos = 0;
+      while (sp) {
+        --sp;
+        const int k = st_node[sp];
+        const int bits = st_bits[sp];
+        const uint32_t code = st_code[sp];
+        const int sym = nsym[k];
+        if (sym >= 0) {
+          acc |= (uint64_t)(1u | ((uint32_t)sym << 1)) << nacc;  // bit 1, then the 9-bit symbol
+          nacc += 10;
+          if (bits > 32) atomicMax(err, 5);
+          s_code[sym] = code;
+          s_len[sym] = (uint8_t)bits;
+        } else {
+          nacc += 1;  // bit 0
+          st_node[sp] = cb[k];
+          st_bits[sp] = (uint8_t)min(bits + 1, 255);
+          st_code[sp] = bits < 32 ? code + (1u << bits) : code;
+          ++sp;
+          st_node[sp] = ca[k];
+          st_bits[sp] = (uint8_t)min(bits + 1, 255);
+          st_code[sp] = code;
+          ++sp;
+        }
+        if (nacc >= 32) {
+          s_tree[wpos++] = (uint32_t)acc;
+          acc >>= 32;
+          nacc -= 32;
+        }
+      }
+      nbits = wpos * 32 + nacc;
+      if (nacc) s_tree[wpos] = (uint32_t)acc;
+    }
+    s_bits = nbits;
+  }
+  __syncthreads();
+  if (t < kSyms) {
+    out->code[t] = s_code[t];
+    out->len[t] = s_len[t];
+  }
+  for (int i = t; i < kTreeBytesMax; i += blockDim.x) out->tree[i] = (uint8_t)(s_tree[i >> 2] >> (8 * (i & 3)));
+  if (t == 0) {
+    out->tree_bits = (uint32_t)s_bits;
+    out->nleaves = (uint32_t)n;
+  }
+}
+
+// ---- K-layout --------------------------------------------------------------------------------
+struct LayoutChunk {
+  const uint32_t *seghist;  // [n][nseg][261]
+  const TreeOut *trees;     // [n]
+  uint32_t *seg_bits;       // [n][nseg] out
+  uint32_t *seg_pos;        // [n][nseg] out: absolute offset of the segment PAYLOAD inside the item
+  const uint8_t *prefix;    // bytes emitted before the chunk (container headers), may be null
+  int prefix_len;
+  int size_patch;           // offset inside the prefix of the u32 chunk size, or -1
+  int nseg;
+  int framed;               // segments carry 2/4-byte size headers (huffman_enc.cpp:340-352)
+};
+struct LayoutParams {
+  LayoutChunk ch[2];
+  int nchunks;
+  int riff_patch;  // patch u32 at item offset 4 with (total - 8)
+  uint8_t *out;
+  unsigned long long out_stride;
+  uint32_t *sizes;  // [n]; 0 = does not fit
+  int *err;
+};
+
+constexpr int kLayoutThreads = 256;
+
+__device__ __forceinline__ void put_u32le(uint8_t *p, uint32_t x) {
+  p[0] = (uint8_t)x;
+  p[1] = (uint8_t)(x >> 8);
+  p[2] = (uint8_t)(x >> 16);
+  p[3] = (uint8_t)(x >> 24);
+}
+
+// grid (n).
+__global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_constant__ LayoutParams P) {
+  __shared__ uint32_t s_lenx[kSyms];
+  __shared__ uint32_t ws[kLayoutThreads / 32 + 1];
+  __shared__ unsigned long long s_chunk_bytes[2];
+  const int item = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  uint8_t *out = P.out + (size_t)item * P.out_stride;
+
+  // pass 1: segment bit lengths and chunk sizes
+  for (int k = 0; k < P.nchunks; ++k) {
+    const LayoutChunk &C = P.ch[k];
+    const TreeOut *tr = C.trees + item;
+    __syncthreads();
+    for (int s = t; s < kSyms; s += blockDim.x) s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+    if (t == 0) s_chunk_bytes[k] = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (int b = wid; b < C.nseg; b += kLayoutThreads / 32) {
+      const uint32_t *h = C.seghist + ((size_t)item * C.nseg + b) * kSyms;
+      unsigned long long bits = 0;
+      for (int s = lane; s < kSyms; s += 32) bits += (unsigned long long)h[s] * s_lenx[s];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+      if (lane == 0) {
+        C.seg_bits[(size_t)item * C.nseg + b] = (uint32_t)bits;
+        const unsigned long long sz = (bits + 7) >> 3;
+        mine += sz + (C.framed ? (sz <= 0x7fff ? 2 : 4) : 0);
+      }
+    }
+    if (lane == 0 && mine) atomicAdd(&s_chunk_bytes[k], mine);
+  }
+  __syncthreads();
+  unsigned long long total = 0;
+  for (int k = 0; k < P.nchunks; ++k)
+    total += (unsigned long long)P.ch[k].prefix_len + ((P.ch[k].trees[item].tree_bits + 7) >> 3) + s_chunk_bytes[k];
+  if (total > P.out_stride || total > 0xffffffffull) {
+    if (t == 0) {
+      P.sizes[item] = 0;
+      atomicMax(P.err, 4);
+    }
+    return;
+  }
+
+  // pass 2: emit prefixes, trees, segment headers; record payload positions
+  uint32_t pos = 0;
+  for (int k = 0; k < P.nchunks; ++k) {
+    const LayoutChunk &C = P.ch[k];
+    const TreeOut *tr = C.trees + item;
+    const uint32_t prefix_at = pos;
+    for (int i = t; i < C.prefix_len; i += blockDim.x) out[pos + i] = C.prefix[i];
+    pos += C.prefix_len;
+    const uint32_t tree_bytes = (tr->tree_bits + 7) >> 3;
+    for (int i = t; i < (int)tree_bytes; i += blockDim.x) out[pos + i] = tr->tree[i];
+    const uint32_t chunk_bytes = tree_bytes + (uint32_t)s_chunk_bytes[k];
+    __syncthreads();  // prefix bytes written before the patch below
+    if (t == 0 && C.size_patch >= 0) put_u32le(out + prefix_at + C.size_patch, chunk_bytes);
+    pos += tree_bytes;
+    // exclusive scan of (header + payload) over the segments, kLayoutThreads at a time
+    uint32_t run = 0;
+    for (int b0 = 0; b0 < C.nseg; b0 += kLayoutThreads) {
+      const int b = b0 + t;
+      uint32_t sz = 0, hdr = 0;
+      if (b < C.nseg) {
+        sz = (C.seg_bits[(size_t)item * C.nseg + b] + 7) >> 3;
+        hdr = C.framed ? (sz <= 0x7fff ? 2u : 4u) : 0u;
+      }
+      uint32_t tot;
+      const uint32_t ex = block_exscan_u32(sz + hdr, ws, &tot);
+      if (b < C.nseg) {
+        uint8_t *h = out + pos + run + ex;
+        if (hdr == 2) {
+          h[0] = (uint8_t)sz;
+          h[1] = (uint8_t)(sz >> 8);
+        } else if (hdr == 4) {
+          const uint32_t lo = (sz & 0x7fff) | 0x8000, hi = sz >> 15;
+          h[0] = (uint8_t)lo;
+          h[1] = (uint8_t)(lo >> 8);
+          h[2] = (uint8_t)hi;
+          h[3] = (uint8_t)(hi >> 8);
+        }
+        C.seg_pos[(size_t)item * C.nseg + b] = pos + run + ex + hdr;
+      }
+      run += tot;
+    }
+    pos += run;
+  }
+  if (t == 0) {
+    P.sizes[item] = pos;
+    if (P.riff_patch) put_u32le(out + 4, pos - 8);
+  }
+}
+
+// ---- K-pack ----------------------------------------------------------------------------------
+struct SizeSink {
+  const uint32_t *lenx;  // len + extra bits per symbol
+  uint32_t bits;
+  __device__ __forceinline__ void tok(int sym, uint32_t, int) { bits += lenx[sym]; }
+};
+
+// Thread-local LSB-first bit accumulator writing into a shared-memory window.  Only tokens whose
+// first bit falls inside [w0, w0 + kWinBits) are written (a token may spill <= 46 bits into the
+// two slack words).
+struct EmitSink {
+  const uint32_t *code;
+  const uint8_t *len;
+  uint32_t *win;
+  uint32_t pos;  // position of the next token, in window coordinates of the whole piece
+  uint32_t w0;
+  uint64_t acc;
+  int nacc;   // bits held in acc; -1 = accumulator not positioned yet
+  int wpos;
+  __device__ __forceinline__ void put(uint32_t v, int n) {
+    acc |= (uint64_t)v << nacc;
+    nacc += n;
+    if (nacc >= 32) {
+      atomicOr(&win[wpos++], (uint32_t)acc);
+      acc >>= 32;
+      nacc -= 32;
+    }
+  }
+  __device__ __forceinline__ void tok(int sym, uint32_t extra, int nextra) {
+    const int l = len[sym];
+    if (pos >= w0 && pos < w0 + (uint32_t)kWinBits) {
+      if (nacc < 0) {
+        const uint32_t rel = pos - w0;
+        nacc = (int)(rel & 31);
+        wpos = (int)(rel >> 5);
+        acc = 0;
+      }
+      if (l) put(code[sym], l);
+      if (nextra) put(extra, nextra);
+    } else if (nacc >= 0) {
+      flush();
+    }
+    pos += (uint32_t)(l + nextra);
+  }
+  __device__ __forceinline__ void flush() {
+    if (nacc > 0) atomicOr(&win[wpos], (uint32_t)acc);
+    nacc = -1;
+  }
+};
+
+// grid (nseg, n).  Dynamic shared memory: (kWinWords + 2) words.
+__global__ void __launch_bounds__(kHuffThreads)
+    k_huff_pack(const uint8_t *__restrict__ in, HuffGeom hg, const TreeOut *__restrict__ trees,
+                const uint32_t *__restrict__ seg_bits, const uint32_t *__restrict__ seg_pos,
+                const uint32_t *__restrict__ sizes, uint8_t *__restrict__ out,
+                unsigned long long out_stride, int *err) {
+  extern __shared__ uint32_t win[];
+  __shared__ uint32_t s_code[kSyms];
+  __shared__ uint8_t s_len[kSyms + 3];
+  __shared__ uint32_t s_lenx[kSyms];
+  __shared__ uint32_t ws[17];
+  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
+  if (sizes[item] == 0) return;  // did not fit (k_huff_layout)
+  const TreeOut *tr = trees + item;
+  for (int s = t; s < kSyms; s += blockDim.x) {
+    s_code[s] = tr->code[s];
+    s_len[s] = tr->len[s];
+    s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+  }
+  for (int i = t; i < kWinWords + 2; i += blockDim.x) win[i] = 0;
+  __syncthreads();
+  const uint8_t *seg = in + (size_t)item * hg.in_stride + (size_t)b * hg.seg_size;
+  uint8_t *dst = out + (size_t)item * out_stride + seg_pos[(size_t)item * hg.nseg + b];
+
+  uint32_t carry = 0;       // zeros of an unfinished run
+  uint32_t gbits = 0;       // bits emitted so far (complete bytes below gbits>>3 are in `dst`)
+  for (int base = 0; base < hg.seg_size; base += kPieceBytes) {
+    const int off = base + t * kChunkBytes;
+    Chunk c;
+    load_chunk(c, seg, hg.seg_size, off);
+    uint32_t carry_out;
+    const uint32_t z_in = block_run_scan(run_summary(c), carry, ws, &carry_out);
+    carry = carry_out;
+    const bool last = c.valid > 0 && off + c.valid == hg.seg_size;
+    SizeSink ss{s_lenx, 0};
+    walk_chunk(c, z_in, last, ss);
+    uint32_t piece_bits;
+    const uint32_t my_start = block_exscan_u32(ss.bits, ws, &piece_bits);
+    // window coordinates: bit 0 of the window = byte boundary at or below gbits
+    const uint32_t lead = gbits & 7;
+    const uint32_t vend = lead + piece_bits;
+    const uint32_t gbyte = gbits >> 3;
+    for (uint32_t w0 = 0; w0 < vend || w0 == 0; w0 += kWinBits) {
+      if (ss.bits && lead + my_start < w0 + (uint32_t)kWinBits && lead + my_start + ss.bits > w0) {
+        EmitSink es{s_code, s_len, win, lead + my_start, w0, 0, -1, 0};
+        walk_chunk(c, z_in, last, es);
+        es.flush();
+      }
+      __syncthreads();
+      const bool last_win = w0 + (uint32_t)kWinBits >= vend;
+      const uint32_t nbytes = last_win ? ((vend - w0) >> 3) : (uint32_t)(kWinBits / 8);
+      const uint8_t *wb = reinterpret_cast<const uint8_t *>(win);
+      uint8_t *o = dst + gbyte + (w0 >> 3);
+      for (uint32_t i = t; i < nbytes; i += blockDim.x) o[i] = wb[i];
+      __syncthreads();
+      // carry the unfinished tail (partial byte, or the slack words) to the front of the window
+      uint32_t c0 = 0, c1 = 0;
+      if (last_win) {
+        c0 = ((vend - w0) & 7) ? wb[nbytes] : 0;
+      } else {
+        c0 = win[kWinWords];
+        c1 = win[kWinWords + 1];
+      }
+      __syncthreads();
+      for (int i = t; i < kWinWords + 2; i += blockDim.x) win[i] = i == 0 ? c0 : (i == 1 ? c1 : 0u);
+      __syncthreads();
+      if (last_win) break;
+    }
+    gbits += piece_bits;
+  }
+  // final partial byte (its padding bits are zero here; k_huff_stale adds the stale ones)
+  if (t == 0) {
+    if (gbits & 7) dst[gbits >> 3] = (uint8_t)win[0];
+    if (gbits != seg_bits[(size_t)item * hg.nseg + b]) atomicMax(err, 99);  // internal consistency
+  }
+}
+
+// ---- K-stale ---------------------------------------------------------------------------------
+// Padding bit p of segment b takes the value WRITTEN at bit p by the most recent earlier segment
+// of the same chunk that is longer than p bits (else 0).  One thread per segment.
+__global__ void k_huff_stale(int n, int nseg, const uint32_t *__restrict__ seg_bits,
+                             const uint32_t *__restrict__ seg_pos, const uint32_t *__restrict__ sizes,
+                             uint8_t *__restrict__ out, unsigned long long out_stride) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n * nseg) return;
+  const int item = (int)(idx / nseg), b = (int)(idx % nseg);
+  if (b == 0 || sizes[item] == 0) return;
+  const uint32_t *bits = seg_bits + (size_t)item * nseg;
+  const uint32_t *pos = seg_pos + (size_t)item * nseg;
+  uint32_t lo = bits[b];
+  const uint32_t hi = (lo + 7) & ~7u;  // exclusive end of the padding
+  if (lo == hi) return;
+  uint8_t *base = out + (size_t)item * out_stride;
+  const uint32_t byte_idx = lo >> 3;
+  uint32_t add = 0;
+  for (int e = b - 1; e >= 0 && lo < hi; --e) {
+    const uint32_t le = bits[e];
+    if (le > lo) {
+      const uint32_t upto = min(le, hi);  // positions [lo, upto) come from segment e
+      const uint32_t mask = ((1u << (upto - (byte_idx << 3))) - 1u) & ~((1u << (lo - (byte_idx << 3))) - 1u);
+      add |= base[pos[e] + byte_idx] & mask;
+      lo = upto;
+    }
+  }
+  if (add) base[pos[b] + byte_idx] |= (uint8_t)add;
+}
+
+}  // namespace himgcu
+
+#endif  // HIMG_B200_HUFF_ENC_KERNELS_CUH_
