@@ -125,6 +125,31 @@ class Context:
                                                  _ptr(out), _ptr(status)))
         return out, status
 
+    # ---- batch, host buffers (numpy arrays or pinned CPU torch tensors) -------------------------
+    def encode_batch_host(self, pixels, quality=50, use_ycbcr=True, out=None, offsets=None, sizes=None):
+        """pixels: host uint8 [n][h][w][nch].  Returns (out u8 buffer, offsets u64 [n+1], sizes u32 [n])."""
+        n, h, w, nch = pixels.shape
+        if out is None:
+            out = np.empty(n * encode_bound(w, h, nch), np.uint8)
+        if offsets is None:
+            offsets = np.empty(n + 1, np.uint64)
+        if sizes is None:
+            sizes = np.empty(n, np.uint32)
+        cap = out.size if isinstance(out, np.ndarray) else out.numel()
+        self._check(self.lib.himgcu_encode_batch_host(self.h, _ptr(pixels), n, w, h, nch, quality, int(use_ycbcr),
+                                                      _ptr(out), cap, _ptr(offsets), _ptr(sizes)))
+        return out, offsets, sizes
+
+    def decode_batch_host(self, himg, offsets, sizes, w, h, nch, flags=STRICT, out=None, status=None):
+        n = (offsets.size if isinstance(offsets, np.ndarray) else offsets.numel()) - 1
+        if out is None:
+            out = np.empty((n, h, w, nch), np.uint8)
+        if status is None:
+            status = np.empty(n, np.int32)
+        self._check(self.lib.himgcu_decode_batch_host(self.h, _ptr(himg), _ptr(offsets), _ptr(sizes), n, w, h, nch, flags,
+                                                      _ptr(out), _ptr(status)))
+        return out, status
+
     # ---- stages (device tensors) ---------------------------------------------------------------
     def stage_lowres(self, pixels, use_ycbcr=True, nch=None):
         import torch

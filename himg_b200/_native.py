@@ -33,6 +33,12 @@ SIGNATURES = {
                                       C.c_size_t, C.c_void_p]),
     "himgcu_decode_batch": (C.c_int, [C.c_void_p, _u8p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, _u8p, C.c_void_p]),
+    "himgcu_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "himgcu_host_free": (None, [C.c_void_p]),
+    "himgcu_encode_batch_host": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
+                                           C.c_size_t, C.c_void_p, C.c_void_p]),
+    "himgcu_decode_batch_host": (C.c_int, [C.c_void_p, _u8p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, _u8p, C.c_void_p]),
     "himgcu_stage_lowres": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]),
     "himgcu_lres_size": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "himgcu_lres_stride": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

@@ -1,7 +1,8 @@
 // C-ABI implementation (include/himg_cuda.h): context, device scratch, launch sequences.
-// Product code: no CPU fallback and nothing from oracle/ is referenced here.
+// Product code: no CPU fallback; the test-only CPU restatement is never linked or called here.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -47,6 +48,7 @@ struct himgcu_ctx {
   std::vector<std::string> prof_names;
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
+  size_t host_sub_bytes = (size_t)4 << 30;  // device memory used per sub-batch of the host-buffer calls
 };
 
 namespace {
@@ -690,6 +692,98 @@ int himgcu_decode(himgcu_ctx *ctx, const uint8_t *himg, size_t size, int flags, 
   if (status) return fail(ctx, HIMGCU_REJECT, "stream rejected");
   CK(cudaMemcpyAsync(out, d_px, g.out_img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return HIMGCU_OK;
+}
+
+// ---- batch with host buffers -------------------------------------------------------------------
+
+void *himgcu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void himgcu_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int w, int h, int nch, int quality,
+                             int use_ycbcr, uint8_t *out, size_t out_cap, uint64_t *offsets, uint32_t *sizes) {
+  if (!ctx || !pixels || !out || !offsets || !sizes || n < 0) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  if (!shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", w, h, nch);
+  CK(cudaSetDevice(ctx->device));
+  const Geom g = make_geom(w, h, nch, nch);
+  const bool ycbcr = use_ycbcr && nch >= 3;
+  const size_t stride = (himgcu_encode_bound(w, h, nch) + 255) & ~(size_t)255;
+  const size_t per = per_image_encode_ws(g) + g.img_bytes + stride;
+  int sub = (int)std::min<size_t>((size_t)std::max(n, 1), std::max<size_t>(1, ctx->host_sub_bytes / per));
+  sub = std::min(sub, 65535);
+  uint8_t *d_in, *d_out;
+  uint32_t *d_sizes;
+  ENSURE("hb_in", (size_t)sub * g.img_bytes, d_in);
+  ENSURE("hb_out", (size_t)sub * stride, d_out);
+  ENSURE("hb_sizes", (size_t)sub * sizeof(uint32_t), d_sizes);
+  uint64_t pos = 0;
+  offsets[0] = 0;
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int m = std::min(sub, n - i0);
+    CK(cudaMemcpyAsync(d_in, pixels + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = encode_device(ctx, d_in, m, g, quality, ycbcr, d_out, stride, d_sizes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(sizes + i0, d_sizes, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < m; ++i) {
+      const uint32_t sz = sizes[i0 + i];
+      if (sz == 0) return fail(ctx, HIMGCU_ERR_CAPACITY, "image %d could not be encoded", i0 + i);
+      if (pos + sz > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small");
+      CK(cudaMemcpyAsync(out + pos, d_out + (size_t)i * stride, sz, cudaMemcpyDeviceToHost, ctx->stream));
+      pos += ((uint64_t)sz + 15) & ~15ull;
+      offsets[i0 + i + 1] = pos;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return HIMGCU_OK;
+}
+
+int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_t *offsets, const uint32_t *sizes,
+                             int n, int w, int h, int nch, int flags, uint8_t *pixels_out, int32_t *status) {
+  if (!ctx || !himg || !offsets || !sizes || !pixels_out || !status || n < 0) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
+  if (!shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", w, h, nch);
+  CK(cudaSetDevice(ctx->device));
+  const Geom g = make_geom(w, h, nch, nch);
+  const size_t stride = (himgcu_encode_bound(w, h, nch) + 255) & ~(size_t)255;
+  const size_t per = per_image_encode_ws(g) + g.out_img_bytes + stride;
+  int sub = (int)std::min<size_t>((size_t)std::max(n, 1), std::max<size_t>(1, ctx->host_sub_bytes / per));
+  sub = std::min(sub, 65535);
+  uint8_t *d_px;
+  unsigned long long *d_off;
+  uint32_t *d_sz;
+  int *d_status;
+  ENSURE("hb_px", (size_t)sub * g.out_img_bytes, d_px);
+  ENSURE("hb_off", (size_t)sub * sizeof(unsigned long long), d_off);
+  ENSURE("hb_sz", (size_t)sub * sizeof(uint32_t), d_sz);
+  ENSURE("hb_status", (size_t)sub * sizeof(int), d_status);
+  std::vector<unsigned long long> rel(sub);
+  for (int i0 = 0; i0 < n; i0 += sub) {
+    const int m = std::min(sub, n - i0);
+    // the sub-batch's streams are copied as one contiguous host range
+    uint64_t lo = offsets[i0], hi = 0;
+    for (int i = 0; i < m; ++i) {
+      lo = std::min<uint64_t>(lo, offsets[i0 + i]);
+      hi = std::max<uint64_t>(hi, offsets[i0 + i] + sizes[i0 + i]);
+    }
+    uint8_t *d_in;
+    ENSURE("hb_himg", (size_t)(hi - lo) + 64, d_in);
+    for (int i = 0; i < m; ++i) rel[i] = offsets[i0 + i] - lo;
+    CK(cudaMemcpyAsync(d_in, himg + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_off, rel.data(), (size_t)m * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_sz, sizes + i0, (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = decode_device(ctx, d_in, d_off, d_sz, m, g, flags, d_px, d_status);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(status + i0, d_status, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pixels_out + (size_t)i0 * g.out_img_bytes, d_px, (size_t)m * g.out_img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `rel` is reused by the next sub-batch
+  }
   return HIMGCU_OK;
 }
 

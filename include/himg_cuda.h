@@ -90,6 +90,21 @@ int himgcu_decode_batch(himgcu_ctx *ctx, const uint8_t *d_himg, const uint64_t *
                         const uint32_t *d_sizes, int n, int width, int height, int num_channels,
                         int flags, uint8_t *d_pixels_out, int32_t *d_status);
 
+/* ---- batch, HOST pointers (what a file/stream based caller uses; basis of the e2e figure) ----
+ * Same work as the device batch calls with the transfers included: pixels (or bitstreams) are
+ * copied host->device in sub-batches, coded, and the results copied back.  Pinned host memory
+ * (himgcu_host_alloc) makes the copies asynchronous; pageable memory works but is slower.
+ * Encode: image i's bitstream lands at out + offsets[i], offsets[n] = total bytes (each stream
+ * is padded to a multiple of 16 bytes; sizes[i] is the exact size). */
+void *himgcu_host_alloc(size_t bytes);
+void himgcu_host_free(void *p);
+int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int width, int height,
+                             int num_channels, int quality, int use_ycbcr, uint8_t *out,
+                             size_t out_cap, uint64_t *offsets /* [n+1] */, uint32_t *sizes /* [n] */);
+int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_t *offsets,
+                             const uint32_t *sizes, int n, int width, int height, int num_channels,
+                             int flags, uint8_t *pixels_out, int32_t *status /* [n] */);
+
 /* ---- stage-level entry points (DEVICE pointers) -------------------------------------------
  * The pipeline stages above are built from these; they are exported for the parity tests and
  * for per-kernel roofline timing.  n = number of images, shapes as above. */
