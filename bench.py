@@ -128,7 +128,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=512, help="images per GPU (weak scaling)")
     ap.add_argument("--e2e-images", type=int, default=128, help="images per GPU for the host-buffer leg")
-    ap.add_argument("--cpu-images-per-core", type=int, default=3)
+    ap.add_argument("--cpu-images-per-core", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -141,7 +141,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        per = max(1, args.cpu_images_per_core)
+        per = max(1, min(args.cpu_images_per_core, 12))  # bounded sample per step
         for _ in range(args.warmup):
             cpu_reference_throughput(1)
         vals, t0 = [], time.perf_counter()

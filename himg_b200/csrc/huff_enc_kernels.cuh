@@ -47,41 +47,54 @@ __device__ __forceinline__ int sym_extra_bits(int s) {
 }
 
 // ---- per-thread chunk of a segment ---------------------------------------------------------
+// The 32 bytes of a thread are loaded with two coalesced 128-bit loads, parked in shared memory
+// with a 9-word row stride (conflict-free for per-lane byte reads), and summarised as a bit mask
+// of non-zero bytes.  Token walks then loop over the SET bits only (3 of 4 coefficient bytes are
+// zero at quality 50), with one compact loop body instead of 32 unrolled byte positions.
+constexpr int kRowWords = 9;
+
 struct Chunk {
-  uint32_t w[8];
-  int valid;  // number of valid bytes (0..32)
+  const uint8_t *row;  // this thread's 36-byte row in shared memory
+  uint32_t nz;         // bit p set <=> byte p is valid and non-zero
+  int valid;           // number of valid bytes (0..32)
 };
 
-__device__ __forceinline__ void load_chunk(Chunk &c, const uint8_t *__restrict__ seg, int seg_size, int off) {
+__device__ __forceinline__ uint32_t nonzero_nibble(uint32_t w) {
+  // high bit of every byte set iff that byte is non-zero, then gather the four bits
+  const uint32_t x = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+  return (((x >> 7) * 0x01020408u) >> 24) & 0xfu;
+}
+
+__device__ __forceinline__ void load_chunk(Chunk &c, uint32_t *rows, const uint8_t *__restrict__ seg,
+                                           int seg_size, int off) {
+  uint32_t w[8];
   c.valid = min(max(seg_size - off, 0), kChunkBytes);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) c.w[k] = 0;
+  for (int k = 0; k < 8; ++k) w[k] = 0;
   if (c.valid == kChunkBytes && ((reinterpret_cast<uintptr_t>(seg + off)) & 15) == 0) {
     const uint4 a = __ldg(reinterpret_cast<const uint4 *>(seg + off));
     const uint4 b = __ldg(reinterpret_cast<const uint4 *>(seg + off) + 1);
-    c.w[0] = a.x; c.w[1] = a.y; c.w[2] = a.z; c.w[3] = a.w;
-    c.w[4] = b.x; c.w[5] = b.y; c.w[6] = b.z; c.w[7] = b.w;
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
   } else {
-#pragma unroll
-    for (int k = 0; k < kChunkBytes; ++k)
-      if (k < c.valid) c.w[k >> 2] |= (uint32_t)seg[off + k] << (8 * (k & 3));
+    for (int k = 0; k < c.valid; ++k) w[k >> 2] |= (uint32_t)seg[off + k] << (8 * (k & 3));
   }
+  uint32_t *row = rows + threadIdx.x * kRowWords;
+  uint32_t nz = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    row[k] = w[k];
+    nz |= nonzero_nibble(w[k]) << (4 * k);
+  }
+  c.row = reinterpret_cast<const uint8_t *>(row);
+  c.nz = nz;  // bytes past `valid` were loaded as zero
 }
 
 // Zero-run summary of a chunk: low 31 bits = trailing zeros, bit 31 = "all zero" (an empty chunk
 // is the identity).  combine(X earlier, Y later) is associative.
 __device__ __forceinline__ uint32_t run_summary(const Chunk &c) {
-  if (c.valid == 0) return 0x80000000u;
-  int tz = 0;
-  bool all = true;
-#pragma unroll
-  for (int k = kChunkBytes - 1; k >= 0; --k) {
-    if (k < c.valid && all) {
-      if (((c.w[k >> 2] >> (8 * (k & 3))) & 0xffu) == 0) ++tz;
-      else all = false;
-    }
-  }
-  return (uint32_t)tz | (all ? 0x80000000u : 0u);
+  if (c.nz == 0) return (uint32_t)c.valid | 0x80000000u;
+  return (uint32_t)(c.valid - 1 - (31 - __clz(c.nz)));
 }
 __device__ __forceinline__ uint32_t run_combine(uint32_t x, uint32_t y) {
   return (y & 0x80000000u) ? (((x & 0x7fffffffu) + (y & 0x7fffffffu)) | (x & 0x80000000u)) : y;
@@ -139,33 +152,21 @@ __device__ __forceinline__ void emit_run(uint32_t z, Sink &s) {
 // z_in: zeros immediately before the chunk; flush_end: the chunk holds the segment's last byte.
 template <class Sink>
 __device__ __forceinline__ void walk_chunk(const Chunk &c, uint32_t z_in, bool flush_end, Sink &s) {
-  uint32_t z = z_in;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (4 * k < c.valid) {
-      const uint32_t word = c.w[k];
-      if (word == 0 && 4 * k + 4 <= c.valid) {
-        z += 4;
-      } else {
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (4 * k + b < c.valid) {
-            const uint32_t byte = (word >> (8 * b)) & 0xffu;
-            if (byte == 0) {
-              ++z;
-            } else {
-              if (z) {
-                emit_run(z, s);
-                z = 0;
-              }
-              s.tok((int)byte, 0, 0);
-            }
-          }
-        }
-      }
-    }
+  uint32_t mask = c.nz, carry = z_in;
+  int prev = -1;
+  while (mask) {
+    const int p = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const uint32_t z = (uint32_t)(p - prev - 1) + carry;
+    carry = 0;
+    prev = p;
+    if (z) emit_run(z, s);
+    s.tok((int)c.row[p], 0, 0);
   }
-  if (flush_end && z) emit_run(z, s);
+  if (flush_end) {
+    const uint32_t z = (uint32_t)(c.valid - 1 - prev) + carry;
+    if (z) emit_run(z, s);
+  }
 }
 
 // ---- K-hist ----------------------------------------------------------------------------------
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(kHuffThreads)
     k_huff_hist(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist) {
   __shared__ uint32_t sh[kSyms];
   __shared__ uint32_t ws[17];
+  __shared__ uint32_t rows[kHuffThreads * kRowWords];
   for (int i = threadIdx.x; i < kSyms; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const uint8_t *seg = in + (size_t)blockIdx.y * hg.in_stride + (size_t)blockIdx.x * hg.seg_size;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(kHuffThreads)
   for (int base = 0; base < hg.seg_size; base += kPieceBytes) {
     const int off = base + threadIdx.x * kChunkBytes;
     Chunk c;
-    load_chunk(c, seg, hg.seg_size, off);
+    load_chunk(c, rows, seg, hg.seg_size, off);
     uint32_t carry_out;
     const uint32_t z_in = block_run_scan(run_summary(c), carry, ws, &carry_out);
     carry = carry_out;
@@ -532,6 +534,7 @@ __global__ void __launch_bounds__(kHuffThreads)
   __shared__ uint8_t s_len[kSyms + 3];
   __shared__ uint32_t s_lenx[kSyms];
   __shared__ uint32_t ws[17];
+  __shared__ uint32_t rows[kHuffThreads * kRowWords];
   const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
   if (sizes[item] == 0) return;  // did not fit (k_huff_layout)
   const TreeOut *tr = trees + item;
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(kHuffThreads)
   for (int base = 0; base < hg.seg_size; base += kPieceBytes) {
     const int off = base + t * kChunkBytes;
     Chunk c;
-    load_chunk(c, seg, hg.seg_size, off);
+    load_chunk(c, rows, seg, hg.seg_size, off);
     uint32_t carry_out;
     const uint32_t z_in = block_run_scan(run_summary(c), carry, ws, &carry_out);
     carry = carry_out;
