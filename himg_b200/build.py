@@ -49,6 +49,40 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(LIBDIR, "libhimg.so")
+DRIVERS = ["chimg", "dhimg", "benchmark"]
+
+
+def build_host(force: bool = False) -> dict:
+    """C++ host layer: libhimg.so (himg::Encoder / himg::Decoder on top of libhimgcu.so) and the
+    chimg / dhimg / benchmark drivers (target names as in the reference's CMake files)."""
+    build(force)
+    srcs = [os.path.join(HOST, "encoder.cpp"), os.path.join(HOST, "decoder.cpp")]
+    deps = srcs + sorted(glob.glob(os.path.join(HOST, "*.h"))) + [LIB]
+    out = {"libhimg": HOST_LIB}
+    common = ["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-fPIC"]
+    rpath = "-Wl,-rpath,$ORIGIN"
+    if force or not os.path.exists(HOST_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOST_LIB) for d in deps):
+        proc = subprocess.run(common + ["-shared", "-o", HOST_LIB] + srcs + ["-L" + LIBDIR, "-lhimgcu", rpath],
+                              capture_output=True, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+            raise RuntimeError("host library build failed")
+    for d in DRIVERS:
+        exe = os.path.join(LIBDIR, d)
+        src = os.path.join(HOST, d + ".cpp")
+        out[d] = exe
+        if force or not os.path.exists(exe) or any(os.path.getmtime(x) > os.path.getmtime(exe) for x in [src, HOST_LIB] + deps):
+            proc = subprocess.run(common + ["-o", exe, src, "-L" + LIBDIR, "-lhimg", "-lhimgcu", rpath],
+                                  capture_output=True, text=True)
+            if proc.returncode != 0:
+                sys.stderr.write(proc.stdout + proc.stderr)
+                raise RuntimeError(f"driver build failed: {d}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True,
                 extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else []))
+    print(build_host(force="--force" in sys.argv))
