@@ -242,6 +242,9 @@ class Context:
             out[name.value.decode()] = (ms.value, cnt.value)
         return out
 
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.himgcu_set_option(self.h, name.encode(), int(value)))
+
     def launch_count(self) -> int:
         return int(self.lib.himgcu_launch_count(self.h))
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "himgcu_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                      C.POINTER(C.c_int)]),
     "himgcu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "himgcu_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
 }
 
 _lib = None

@@ -14,6 +14,7 @@
 #include "huff_dec_kernels.cuh"
 #include "huff_enc_kernels.cuh"
 #include "tables.h"
+#include "xform_fwd2.cuh"
 #include "xform_kernels.cuh"
 
 using namespace himgcu;
@@ -39,6 +40,7 @@ struct himgcu_ctx {
   std::string err;
   std::map<std::string, DevBuf> bufs;
   DevBuf full_lut;  // 7616-byte |x| -> code LUT, uploaded once
+  DevBuf signed_lut;  // 32 KiB signed LUT (index m + 16384) for k_forward2
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   bool profile = false;
@@ -48,7 +50,8 @@ struct himgcu_ctx {
   std::vector<std::string> prof_names;
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
-  size_t host_sub_bytes = (size_t)4 << 30;  // device memory used per sub-batch of the host-buffer calls
+  size_t host_sub_bytes = (size_t)4 << 30;
+  bool force_generic = false;  // tests: route everything through the generic kernels  // device memory used per sub-batch of the host-buffer calls
 };
 
 namespace {
@@ -192,6 +195,74 @@ int upload_full_lut(himgcu_ctx *ctx) {
   return HIMGCU_OK;
 }
 
+int upload_signed_lut(himgcu_ctx *ctx) {
+  if (ctx->signed_lut.p) return HIMGCU_OK;
+  std::vector<uint8_t> lut(2 * kLutCenter);
+  const uint8_t *mag = FullMapLut();
+  for (int v = 0; v < 2 * kLutCenter; ++v) {
+    const int m = v - kLutCenter, a = m < 0 ? -m : m;
+    const int code = mag[a < kFullMapLutSize ? a : kFullMapLutSize - 1];  // >= 7608 -> 127
+    lut[v] = (uint8_t)(m >= 0 ? code : (256 - code) & 0xff);
+  }
+  CK(cudaMalloc(&ctx->signed_lut.p, lut.size()));
+  ctx->signed_lut.cap = lut.size();
+  CK(cudaMemcpyAsync(ctx->signed_lut.p, lut.data(), lut.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return HIMGCU_OK;
+}
+
+// dp4a weights of channel c: coef[k] multiplies byte k of the pixel.
+void make_colour(int nch, bool ycbcr, Fwd2Params *P) {
+  for (int c = 0; c < 4; ++c) {
+    int coef[4] = {0, 0, 0, 0}, add = 0, shr = 0;
+    if (ycbcr && nch >= 3 && c < 3) {
+      if (c == 0) { coef[0] = 1; coef[1] = 2; coef[2] = 1; add = 2; shr = 2; }
+      if (c == 1) { coef[1] = -1; coef[2] = 1; add = 256; shr = 1; }
+      if (c == 2) { coef[0] = 1; coef[1] = -1; add = 256; shr = 1; }
+    } else {
+      coef[c] = 1;
+    }
+    ColourW &w = P->cw[c];
+    w.add = add;
+    w.shr = shr;
+    for (int sh = 0; sh < 4; ++sh) {
+      uint32_t w0 = 0, w1 = 0;
+      for (int k = 0; k < nch && k < 4; ++k) {
+        const int pos = sh + k;
+        const uint32_t byte = (uint32_t)(coef[k] & 0xff);
+        if (pos < 4) w0 |= byte << (8 * pos);
+        else w1 |= byte << (8 * (pos - 4));
+      }
+      w.w0[sh] = (int)w0;
+      w.w1[sh] = (int)w1;
+    }
+  }
+}
+
+bool make_quant_packed(const EncodeTables &t, QuantPacked *q) {
+  // value range after the shift: |T| <= 16320, so |m| <= (16320 + round) >> shift
+  int half = 1;
+  for (int cls = 0; cls < 2; ++cls)
+    for (int j = 0; j < 64; ++j) {
+      const int s = cls ? t.shift_chroma[j] : t.shift_luma[j];
+      if (s > 14) return false;
+      half = std::max(half, ((16320 + (s ? 1 << (s - 1) : 0)) >> s) + 1);
+    }
+  half = std::min((half + 63) & ~63, kLutCenter - 1);
+  q->lut_half = half;
+  for (int cls = 0; cls < 2; ++cls)
+    for (int j = 0; j < 64; ++j) {
+      const int s = cls ? t.shift_chroma[j] : t.shift_luma[j];
+      const uint32_t rep = 0x00010001u;
+      q->shift[cls][j] = s;
+      q->c2[cls][j] = (s ? (1u << (s - 1)) - 1u : 0u) * rep;
+      q->tmask[cls][j] = s ? rep : 0u;
+      q->smask[cls][j] = (0xffffu >> s) * rep;
+      q->off2[cls][j] = (uint32_t)(half - (16384 >> s)) * rep;
+    }
+  return true;
+}
+
 QuantParams make_quant(const EncodeTables &t) {
   QuantParams q;
   for (int j = 0; j < 64; ++j) {
@@ -271,8 +342,39 @@ int launch_fwd(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int
   return HIMGCU_OK;
 }
 
+template <int NCH>
+int launch_fwd2(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
+                const Fwd2Params &P, uint8_t *d_planes) {
+  dim3 grid((g.cols + kFwd2Blocks - 1) / kFwd2Blocks, g.rows, n);
+  const int smem = 8 * kFwd2Blocks * 8 * NCH + ((2 * P.q.lut_half + 1 + 15) & ~15);
+  const uint8_t *lut = (const uint8_t *)ctx->signed_lut.p;
+  if (ycbcr) {
+    CK(cudaFuncSetAttribute(k_forward2<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LAUNCH("k_forward", (k_forward2<NCH, true>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
+  } else {
+    CK(cudaFuncSetAttribute(k_forward2<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LAUNCH("k_forward", (k_forward2<NCH, false>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
+  }
+  return HIMGCU_OK;
+}
+
 int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g,
                   const EncodeTables &t, uint8_t *d_planes) {
+  // fast path: whole 16-pixel-wide block pairs, tightly packed pixels, 16-byte aligned rows
+  if (!ctx->force_generic && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
+    Fwd2Params P;
+    if (make_quant_packed(t, &P.q)) {
+      int rc = upload_signed_lut(ctx);
+      if (rc) return rc;
+      make_colour(g.nch, t.ycbcr, &P);
+      switch (g.nch) {
+        case 1: return launch_fwd2<1>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
+        case 3: return launch_fwd2<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+        default: return launch_fwd2<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+      }
+    }
+  }
   int rc = upload_full_lut(ctx);
   if (rc) return rc;
   const QuantParams qp = make_quant(t);
@@ -515,6 +617,7 @@ void himgcu_destroy(himgcu_ctx *ctx) {
   for (auto &kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
   if (ctx->full_lut.p) cudaFree(ctx->full_lut.p);
+  if (ctx->signed_lut.p) cudaFree(ctx->signed_lut.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -926,5 +1029,14 @@ int himgcu_profile_get(himgcu_ctx *ctx, int index, const char **name, double *to
 }
 
 uint64_t himgcu_launch_count(himgcu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int himgcu_set_option(himgcu_ctx *ctx, const char *name, long long value) {
+  if (!ctx || !name) return HIMGCU_ERR_ARG;
+  if (!strcmp(name, "force_generic")) ctx->force_generic = value != 0;
+  else if (!strcmp(name, "max_workspace_bytes")) ctx->max_workspace = (size_t)value;
+  else if (!strcmp(name, "host_sub_batch_bytes")) ctx->host_sub_bytes = (size_t)value;
+  else return fail(ctx, HIMGCU_ERR_ARG, "unknown option %s", name);
+  return HIMGCU_OK;
+}
 
 }  // extern "C"

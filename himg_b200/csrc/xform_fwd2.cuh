@@ -1,0 +1,256 @@
+// K-fwd, fast path (v2): the roofline kernel of the encoder.
+//
+// Same arithmetic as k_forward (xform_kernels.cuh) -- colour map + low-res subtract + rows/cols WHT
+// + sign-magnitude shift quantise + 8-bit map + coefficient-planar scatter (encoder.cpp:275-328) --
+// restructured for instruction count and latency:
+//
+//  * the 8 pixel rows of a 256-block tile are staged in shared memory by ONE thread with
+//    cp.async.bulk (TMA bulk copy, completion on an mbarrier): HBM reads are fully asynchronous and
+//    perfectly coalesced, 4 CTAs/SM keep ~190 KB in flight per SM;
+//  * a thread owns TWO horizontally adjacent 8x8 blocks and keeps them as 16-bit lane pairs in one
+//    32-bit register (lo = block A, hi = block B).  Lanes carry a bias (256 after the low-res
+//    subtract, doubling per butterfly stage up to 16384) so they stay non-negative: ordinary 32-bit
+//    IADD / IADD3 then act as exact 2-wide SIMD adds and subtracts with no cross-lane borrow;
+//  * colour mapping uses dp4a straight on the interleaved RGB words (no per-byte unpacking);
+//  * the sign-magnitude rounding shift is done on both lanes at once; the 8-bit mapping is one
+//    lookup in a SIGNED table (global memory, L1 resident) indexed by m + 16384;
+//  * the two codes of a lane pair are adjacent bytes of a coefficient plane: one 16-bit store per
+//    pair, 64 contiguous bytes per warp instruction.
+//
+// Preconditions (checked on the host, otherwise k_forward handles the image): pixel_stride == nch,
+// width % 16 == 0, height % 8 == 0, 16-byte aligned pixel base, all shifts <= 14, nch in {1,3}.
+#ifndef HIMG_B200_XFORM_FWD2_CUH_
+#define HIMG_B200_XFORM_FWD2_CUH_
+
+#include "common.cuh"
+
+namespace himgcu {
+
+constexpr int kFwd2Blocks = 256;   // blocks per tile (2 per thread)
+constexpr int kFwd2Threads = 128;
+constexpr int kLutCenter = 16384;  // signed map LUT: index = m + kLutCenter, m in [-16384, 16383]
+
+struct QuantPacked {          // [class][coefficient]; every word is a 16-bit pattern replicated twice
+  uint32_t c2[2][64];         // (shift ? round - 1 : 0)
+  uint32_t tmask[2][64];      // shift ? 0x00010001 : 0      (negative values round half away from 0)
+  uint32_t smask[2][64];      // 0xffff >> shift
+  uint32_t off2[2][64];       // lut_half - (16384 >> shift): re-centres the lane on the shared LUT
+  int shift[2][64];
+  int lut_half;               // the shared-memory LUT covers m in [-lut_half, lut_half]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// packed nine-tap midpoint interpolation on two lanes (values 0..255 per lane)
+__device__ __forceinline__ uint32_t mid2(uint32_t a, uint32_t b) { return ((a + b + 0x00010001u) >> 1) & 0x00ff00ffu; }
+__device__ __forceinline__ void nine2(uint32_t a, uint32_t b, uint32_t (&t)[9]) {
+  t[0] = a;
+  t[8] = b;
+  t[4] = mid2(t[0], t[8]);
+  t[2] = mid2(t[0], t[4]);
+  t[6] = mid2(t[4], t[8]);
+  t[1] = mid2(t[0], t[2]);
+  t[3] = mid2(t[2], t[4]);
+  t[5] = mid2(t[4], t[6]);
+  t[7] = mid2(t[6], t[8]);
+}
+
+// One butterfly level on biased lane pairs: sum doubles the bias, difference gets +2*bias so both
+// outputs carry bias 2B.  K = 2B replicated in both lanes.
+template <uint32_t K>
+__device__ __forceinline__ void bfly(uint32_t a, uint32_t b, uint32_t &s, uint32_t &d) {
+  s = a + b;
+  d = a - b + K;
+}
+
+// 8-point sequency-ordered WHT on lane pairs whose bias is B on entry (8B on exit).
+template <uint32_t B>
+__device__ __forceinline__ void wht8p(uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3, uint32_t &x4,
+                                      uint32_t &x5, uint32_t &x6, uint32_t &x7) {
+  constexpr uint32_t K1 = (2 * B) * 0x00010001u, K2 = (4 * B) * 0x00010001u, K3 = (8 * B) * 0x00010001u;
+  uint32_t a0, a1, a2, a3, a4, a5, a6, a7, b0, b1, b2, b3, b4, b5, b6, b7;
+  bfly<K1>(x0, x4, a0, a4);
+  bfly<K1>(x1, x5, a1, a5);
+  bfly<K1>(x2, x6, a2, a6);
+  bfly<K1>(x3, x7, a3, a7);
+  bfly<K2>(a0, a2, b0, b2);
+  bfly<K2>(a1, a3, b1, b3);
+  bfly<K2>(a4, a6, b4, b6);
+  bfly<K2>(a5, a7, b5, b7);
+  bfly<K3>(b0, b1, x0, x7);
+  bfly<K3>(b4, b5, x1, x6);
+  bfly<K3>(b6, b7, x2, x5);
+  bfly<K3>(b2, b3, x3, x4);
+}
+
+// Colour mapping as dp4a weights: value = (sum_b byte[b] * weight[b] + add) >> shr over the (at
+// most two) words that hold the pixel.  One code path serves Y / Cb / Cr, plain channel extraction
+// and alpha, so the kernel body exists once and the channel loop is not unrolled.
+struct ColourW {
+  int w0[4], w1[4];  // weights for the pixel's first / second word, indexed by (byte offset & 3)
+  int add, shr;
+};
+struct Fwd2Params {
+  QuantPacked q;
+  ColourW cw[4];
+};
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Colour-mapped value pair (lo = block A pixel i, hi = block B pixel i).  wa / wb: the 2*NCH raw
+// row words of the two blocks.
+template <int NCH>
+__device__ __forceinline__ uint32_t colour_pair(const uint32_t *wa, const uint32_t *wb, int i, const int (&cw0)[4],
+                                                const int (&cw1)[4], int add, int shr) {
+  const int k = i * NCH, w0 = k >> 2, sh = k & 3;
+  if (NCH == 1) return __byte_perm(wa[w0], wb[w0], 0x0400 | sh | ((sh + 4) << 8)) & 0x00ff00ffu;
+  int sa = dp4a_us(wa[w0], cw0[sh], add), sb = dp4a_us(wb[w0], cw0[sh], add);
+  if (sh + NCH > 4) {
+    sa = dp4a_us(wa[w0 + 1], cw1[sh], sa);
+    sb = dp4a_us(wb[w0 + 1], cw1[sh], sb);
+  }
+  return (((uint32_t)sa + ((uint32_t)sb << 16)) >> shr) & 0x00ff00ffu;
+}
+
+// Quantise + map + store the 64 lane pairs of one channel.  CLS is compile time so that every
+// per-coefficient constant is a direct constant-bank operand.
+template <int CLS>
+__device__ __forceinline__ void quant_store(const uint32_t (&x)[64], const QuantPacked &qp, const uint8_t *slut,
+                                            uint8_t *dst, int cols) {
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    // lane = T + 16384.  Sign-magnitude rounding: (T + r - [T < 0]) >> s, and [T >= 0] is bit 14.
+    const uint32_t z = x[j];
+    const uint32_t tz = (z >> 14) & qp.tmask[CLS][j];
+    const uint32_t m = (((z + qp.c2[CLS][j] + tz) >> qp.shift[CLS][j]) & qp.smask[CLS][j]) + qp.off2[CLS][j];
+    const uint32_t ca = slut[m & 0xffffu], cb = slut[m >> 16];
+    *reinterpret_cast<uint16_t *>(dst + (size_t)scan_pos(j) * cols) = (uint16_t)(ca | (cb << 8));
+  }
+}
+
+// grid (ceil(cols/256), rows, n), block 128, dynamic smem 8 * 256*8*NCH bytes.
+template <int NCH, bool YCBCR>
+__global__ void __launch_bounds__(kFwd2Threads, 4)
+    k_forward2(const uint8_t *__restrict__ pixels, const uint8_t *__restrict__ L, Geom g,
+               const __grid_constant__ Fwd2Params prm, const uint8_t *__restrict__ slut,
+               uint8_t *__restrict__ planes) {
+  extern __shared__ __align__(128) uint8_t tile[];
+  __shared__ uint64_t bar;
+  constexpr int kRowPitch = kFwd2Blocks * 8 * NCH;
+  uint8_t *lut = tile + 8 * kRowPitch;  // signed map LUT, 2*lut_half + 1 bytes
+  const int v = blockIdx.y, u0 = blockIdx.x * kFwd2Blocks;
+  const int nblk = min(kFwd2Blocks, g.cols - u0);  // even
+  const uint8_t *img = pixels + (size_t)blockIdx.z * g.img_bytes;
+
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t row_bytes = (uint32_t)nblk * 8 * NCH;
+    mbar_expect_tx(&bar, row_bytes * 8);
+#pragma unroll
+    for (int y = 0; y < 8; ++y)
+      bulk_g2s(tile + y * kRowPitch, img + ((size_t)(8 * v + y) * g.w + (size_t)u0 * 8) * NCH, row_bytes, &bar);
+  }
+  {  // copy the needed window of the signed LUT while the tile is in flight
+    const int half = prm.q.lut_half, nw = (2 * half + 1 + 3) >> 2;
+    const uint8_t *src = slut + (kLutCenter - half);
+    for (int i = threadIdx.x; i < nw; i += kFwd2Threads) {
+      uint32_t wv = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) wv |= (uint32_t)__ldg(src + min(4 * i + b, 2 * half)) << (8 * b);
+      reinterpret_cast<uint32_t *>(lut)[i] = wv;
+    }
+  }
+  __syncthreads();
+  const int ub = 2 * threadIdx.x;  // first of this thread's two blocks, tile relative
+  const bool active = ub < nblk;
+  const int u = u0 + ub;
+  uint8_t *seg = planes + (size_t)blockIdx.z * g.planes_bytes + (size_t)v * g.seg + u;
+  mbar_wait(&bar, 0);
+  if (!active) return;
+
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t x[64];
+    int cw0[4], cw1[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cw0[k] = prm.cw[c].w0[k];
+      cw1[k] = prm.cw[c].w1[k];
+    }
+    const int cadd = prm.cw[c].add, cshr = prm.cw[c].shr;
+    // ---- low-res corners of both blocks (columns u, u+1, u+2; rows v, v+1), packed per lane
+    uint32_t lf[9], rt[9];
+    {
+      const uint8_t *Lc = L + ((size_t)blockIdx.z * NCH + c) * g.rows * g.cols;
+      const int v2 = min(v + 1, g.rows - 1), ua = u, ubb = min(u + 1, g.cols - 1), uc = min(u + 2, g.cols - 1);
+      const uint32_t t0 = __ldg(Lc + v * g.cols + ua), t1 = __ldg(Lc + v * g.cols + ubb), t2 = __ldg(Lc + v * g.cols + uc);
+      const uint32_t b0 = __ldg(Lc + v2 * g.cols + ua), b1 = __ldg(Lc + v2 * g.cols + ubb), b2 = __ldg(Lc + v2 * g.cols + uc);
+      nine2(t0 | (t1 << 16), b0 | (b1 << 16), lf);  // left columns of A (lo) and B (hi)
+      nine2(t1 | (t2 << 16), b1 | (b2 << 16), rt);  // right columns
+    }
+    // ---- rows: colour map, subtract the interpolated low-res row (bias 256), row WHT
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const uint4 *rp = reinterpret_cast<const uint4 *>(tile + y * kRowPitch + ub * 8 * NCH);
+      uint32_t w[4 * NCH];  // block A words then block B words
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        const uint4 q = rp[k];
+        w[4 * k] = q.x;
+        w[4 * k + 1] = q.y;
+        w[4 * k + 2] = q.z;
+        w[4 * k + 3] = q.w;
+      }
+      uint32_t t[9];
+      nine2(lf[y], rt[y], t);
+      const uint32_t *wa = w, *wb = w + 2 * NCH;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[y * 8 + i] = colour_pair<NCH>(wa, wb, i, cw0, cw1, cadd, cshr) - t[i] + 0x01000100u;
+      wht8p<256>(x[y * 8 + 0], x[y * 8 + 1], x[y * 8 + 2], x[y * 8 + 3], x[y * 8 + 4], x[y * 8 + 5], x[y * 8 + 6], x[y * 8 + 7]);
+    }
+    // ---- columns (bias 2048 -> 16384)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      wht8p<2048>(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
+    // ---- quantise both lanes, map, store the code pair
+    uint8_t *dst = seg + (size_t)c * g.cols * 64;
+    if (YCBCR && NCH >= 3 && (c == 1 || c == 2)) quant_store<1>(x, prm.q, lut, dst, g.cols);
+    else quant_store<0>(x, prm.q, lut, dst, g.cols);
+  }
+}
+
+}  // namespace himgcu
+
+#endif  // HIMG_B200_XFORM_FWD2_CUH_

@@ -163,6 +163,9 @@ int himgcu_profile_count(himgcu_ctx *ctx);
 int himgcu_profile_get(himgcu_ctx *ctx, int index, const char **name, double *total_ms, int *launches);
 /* Total number of kernels launched through this context since creation. */
 uint64_t himgcu_launch_count(himgcu_ctx *ctx);
+/* Tuning / test knobs: "force_generic" (1 = always use the generic kernels instead of the aligned
+ * fast paths), "max_workspace_bytes", "host_sub_batch_bytes". */
+int himgcu_set_option(himgcu_ctx *ctx, const char *name, long long value);
 
 #ifdef __cplusplus
 }
