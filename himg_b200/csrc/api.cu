@@ -51,7 +51,9 @@ struct himgcu_ctx {
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
   size_t host_sub_bytes = (size_t)4 << 30;
-  bool force_generic = false;  // tests: route everything through the generic kernels  // device memory used per sub-batch of the host-buffer calls
+  bool force_generic = false;  // tests: route everything through the generic kernels
+  // small table uploads are cached by key so that steady-state calls issue no host sync
+  std::string qrec_key, lowres_key, prefix_key;  // device memory used per sub-batch of the host-buffer calls
 };
 
 namespace {
@@ -86,6 +88,9 @@ int ensure(himgcu_ctx *ctx, const char *name, size_t bytes, void **out) {
     const size_t want = (bytes + 255) & ~(size_t)255;
     CK(cudaMalloc(&b.p, want));
     b.cap = want;
+    ctx->qrec_key.clear();
+    ctx->lowres_key.clear();
+    ctx->prefix_key.clear();
   }
   *out = b.p;
   return HIMGCU_OK;
@@ -197,7 +202,7 @@ int upload_full_lut(himgcu_ctx *ctx) {
 
 int upload_signed_lut(himgcu_ctx *ctx) {
   if (ctx->signed_lut.p) return HIMGCU_OK;
-  std::vector<uint8_t> lut(2 * kLutCenter);
+  std::vector<uint8_t> lut(2 * kLutCenter + 64, 0);  // padded: the kernel copies whole 16-byte words
   const uint8_t *mag = FullMapLut();
   for (int v = 0; v < 2 * kLutCenter; ++v) {
     const int m = v - kLutCenter, a = m < 0 ? -m : m;
@@ -239,7 +244,7 @@ void make_colour(int nch, bool ycbcr, Fwd2Params *P) {
   }
 }
 
-bool make_quant_packed(const EncodeTables &t, QuantPacked *q) {
+bool make_quant_packed(const EncodeTables &t, QuantPacked *q, int *lut_half) {
   // value range after the shift: |T| <= 16320, so |m| <= (16320 + round) >> shift
   int half = 1;
   for (int cls = 0; cls < 2; ++cls)
@@ -248,17 +253,20 @@ bool make_quant_packed(const EncodeTables &t, QuantPacked *q) {
       if (s > 14) return false;
       half = std::max(half, ((16320 + (s ? 1 << (s - 1) : 0)) >> s) + 1);
     }
-  half = std::min((half + 63) & ~63, kLutCenter - 1);
-  q->lut_half = half;
+  half = std::min((half + 63) & ~63, kLutCenter - 64);
+  *lut_half = half;
+  memset(q, 0, sizeof(*q));
   for (int cls = 0; cls < 2; ++cls)
-    for (int j = 0; j < 64; ++j) {
+    for (int i = 0; i < 64; ++i) {
+      const int j = scan_coef(i);  // records are stored in scan order
       const int s = cls ? t.shift_chroma[j] : t.shift_luma[j];
       const uint32_t rep = 0x00010001u;
-      q->shift[cls][j] = s;
-      q->c2[cls][j] = (s ? (1u << (s - 1)) - 1u : 0u) * rep;
-      q->tmask[cls][j] = s ? rep : 0u;
-      q->smask[cls][j] = (0xffffu >> s) * rep;
-      q->off2[cls][j] = (uint32_t)(half - (16384 >> s)) * rep;
+      QuantRec &r = q->rec[cls][i];
+      r.shift = (uint32_t)s;
+      r.c2 = (s ? (1u << (s - 1)) - 1u : 0u) * rep;
+      r.tmask = s ? rep : 0u;
+      r.smask = (0xffffu >> s) * rep;
+      r.off2 = (uint32_t)(half - (16384 >> s)) * rep;
     }
   return true;
 }
@@ -315,8 +323,12 @@ int upload_lowres_tables(himgcu_ctx *ctx, const EncodeTables *enc, const int16_t
   }
   LowResTables *d;
   ENSURE("lowres_tables", sizeof(LowResTables), d);
-  CK(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));  // `h` lives on this stack frame
+  const std::string key = enc ? "q" + std::to_string(enc->quality) : std::string();
+  if (key.empty() || ctx->lowres_key != key) {
+    CK(cudaMemcpyAsync(d, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `h` lives on this stack frame
+    ctx->lowres_key = key;
+  }
   *d_out = d;
   return HIMGCU_OK;
 }
@@ -344,16 +356,17 @@ int launch_fwd(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int
 
 template <int NCH>
 int launch_fwd2(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
-                const Fwd2Params &P, uint8_t *d_planes) {
-  dim3 grid((g.cols + kFwd2Blocks - 1) / kFwd2Blocks, g.rows, n);
-  const int smem = 8 * kFwd2Blocks * 8 * NCH + ((2 * P.q.lut_half + 1 + 15) & ~15);
+                const Fwd2Params &P, const QuantPacked *d_q, uint8_t *d_planes) {
+  dim3 grid((g.cols + P.tile_cols - 1) / P.tile_cols, (g.rows + P.tile_rows - 1) / P.tile_rows, n);
+  const int smem = P.tile_rows * 8 * P.tile_cols * 8 * NCH + (int)sizeof(QuantPacked) + ((2 * P.lut_half + 1 + 15) & ~15) +
+                   ((NCH * (P.tile_rows + 1) * (P.tile_cols + 2) + 15) & ~15);
   const uint8_t *lut = (const uint8_t *)ctx->signed_lut.p;
   if (ycbcr) {
     CK(cudaFuncSetAttribute(k_forward2<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LAUNCH("k_forward", (k_forward2<NCH, true>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
+    LAUNCH("k_forward", (k_forward2<NCH, true>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, d_q, lut, d_planes);
   } else {
     CK(cudaFuncSetAttribute(k_forward2<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LAUNCH("k_forward", (k_forward2<NCH, false>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
+    LAUNCH("k_forward", (k_forward2<NCH, false>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, d_q, lut, d_planes);
   }
   return HIMGCU_OK;
 }
@@ -364,14 +377,30 @@ int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, 
   if (!ctx->force_generic && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
       (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
     Fwd2Params P;
-    if (make_quant_packed(t, &P.q)) {
+    QuantPacked hq;
+    if (make_quant_packed(t, &hq, &P.lut_half)) {
       int rc = upload_signed_lut(ctx);
       if (rc) return rc;
       make_colour(g.nch, t.ycbcr, &P);
+      // tile: up to 512 blocks per CTA; narrow images stack block rows so the CTA stays full
+      P.tile_cols = std::min(g.cols, kFwd2Blocks);
+      P.tile_rows = std::max(1, std::min(kFwd2Blocks / P.tile_cols, g.rows));
+      if (g.cols > kFwd2Blocks) {  // balance the column tiles
+        const int nt = (g.cols + kFwd2Blocks - 1) / kFwd2Blocks;
+        P.tile_cols = (((g.cols + nt - 1) / nt) + 1) & ~1;
+      }
+      QuantPacked *d_q;
+      ENSURE("fwd2_qrecs", sizeof(QuantPacked), d_q);
+      const std::string key = std::to_string(t.quality) + (t.ycbcr ? "y" : "n");
+      if (ctx->qrec_key != key) {
+        CK(cudaMemcpyAsync(d_q, &hq, sizeof(hq), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // `hq` is a local
+        ctx->qrec_key = key;
+      }
       switch (g.nch) {
-        case 1: return launch_fwd2<1>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
-        case 3: return launch_fwd2<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
-        default: return launch_fwd2<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+        case 1: return launch_fwd2<1>(ctx, d_pixels, d_L, n, g, false, P, d_q, d_planes);
+        case 3: return launch_fwd2<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_q, d_planes);
+        default: return launch_fwd2<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_q, d_planes);
       }
     }
   }
@@ -434,8 +463,12 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     ENSURE("enc_prefix", prefix_total, d_prefix);
     std::vector<uint8_t> all;
     for (int k = 0; k < nchunks; ++k) all.insert(all.end(), chunks[k].prefix.begin(), chunks[k].prefix.end());
-    CK(cudaMemcpyAsync(d_prefix, all.data(), all.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // `all` is a local
+    const std::string key(all.begin(), all.end());
+    if (ctx->prefix_key != key) {
+      CK(cudaMemcpyAsync(d_prefix, all.data(), all.size(), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));  // `all` is a local
+      ctx->prefix_key = key;
+    }
   }
   size_t prefix_off = 0;
   TreeOut *d_trees[2];

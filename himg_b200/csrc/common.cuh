@@ -52,6 +52,13 @@ __host__ __device__ constexpr int scan_pos(int j) {
   return r == k ? k * k + c : k * k + k + (k - r);
 }
 
+__host__ __device__ constexpr int scan_coef(int i) {
+  // inverse of scan_pos: the coefficient (8*row + col) at scan position i
+  for (int j = 0; j < 64; ++j)
+    if (scan_pos(j) == i) return j;
+  return 0;
+}
+
 __device__ __forceinline__ int clamp255(int x) { return min(max(x, 0), 255); }
 
 // Sequency-ordered 8-point Walsh-Hadamard butterflies (hadamard.cpp:18-44), in place.

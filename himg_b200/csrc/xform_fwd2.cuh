@@ -22,21 +22,29 @@
 #ifndef HIMG_B200_XFORM_FWD2_CUH_
 #define HIMG_B200_XFORM_FWD2_CUH_
 
+#include <utility>
+
 #include "common.cuh"
 
 namespace himgcu {
 
-constexpr int kFwd2Blocks = 256;   // blocks per tile (2 per thread)
-constexpr int kFwd2Threads = 128;
+constexpr int kFwd2Threads = 256;
+constexpr int kFwd2Blocks = 2 * kFwd2Threads;  // 8x8 blocks per CTA tile (2 per thread)
 constexpr int kLutCenter = 16384;  // signed map LUT: index = m + kLutCenter, m in [-16384, 16383]
 
-struct QuantPacked {          // [class][coefficient]; every word is a 16-bit pattern replicated twice
-  uint32_t c2[2][64];         // (shift ? round - 1 : 0)
-  uint32_t tmask[2][64];      // shift ? 0x00010001 : 0      (negative values round half away from 0)
-  uint32_t smask[2][64];      // 0xffff >> shift
-  uint32_t off2[2][64];       // lut_half - (16384 >> shift): re-centres the lane on the shared LUT
-  int shift[2][64];
-  int lut_half;               // the shared-memory LUT covers m in [-lut_half, lut_half]
+// Per-coefficient quantiser record; every mask/constant is a 16-bit pattern replicated in both
+// lanes.  The records live in global memory ([class][scan position]) and are copied to shared
+// memory by each CTA, so the kernel has ONE quantiser body for luma and chroma.
+struct QuantRec {
+  uint32_t c2;     // shift ? round - 1 : 0
+  uint32_t tmask;  // shift ? 0x00010001 : 0      (negative values round half away from 0)
+  uint32_t smask;  // 0xffff >> shift
+  uint32_t off2;   // lut_half - (16384 >> shift): re-centres the lane on the shared LUT
+  uint32_t shift;
+  uint32_t pad[3];
+};
+struct QuantPacked {
+  QuantRec rec[2][64];  // indexed by SCAN position
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,8 +126,10 @@ struct ColourW {
   int add, shr;
 };
 struct Fwd2Params {
-  QuantPacked q;
   ColourW cw[4];
+  int lut_half;    // the shared-memory LUT covers m in [-lut_half, lut_half]
+  int tile_cols;   // blocks per tile row (even, <= 512)
+  int tile_rows;   // block rows per tile (tile_rows * tile_cols <= 512)
 };
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
@@ -143,111 +153,134 @@ __device__ __forceinline__ uint32_t colour_pair(const uint32_t *wa, const uint32
   return (((uint32_t)sa + ((uint32_t)sb << 16)) >> shr) & 0x00ff00ffu;
 }
 
-// Quantise + map + store the 64 lane pairs of one channel.  CLS is compile time so that every
-// per-coefficient constant is a direct constant-bank operand.
-template <int CLS>
-__device__ __forceinline__ void quant_store(const uint32_t (&x)[64], const QuantPacked &qp, const uint8_t *slut,
-                                            uint8_t *dst, int cols) {
-#pragma unroll
-  for (int j = 0; j < 64; ++j) {
-    // lane = T + 16384.  Sign-magnitude rounding: (T + r - [T < 0]) >> s, and [T >= 0] is bit 14.
-    const uint32_t z = x[j];
-    const uint32_t tz = (z >> 14) & qp.tmask[CLS][j];
-    const uint32_t m = (((z + qp.c2[CLS][j] + tz) >> qp.shift[CLS][j]) & qp.smask[CLS][j]) + qp.off2[CLS][j];
-    const uint32_t ca = slut[m & 0xffffu], cb = slut[m >> 16];
-    *reinterpret_cast<uint16_t *>(dst + (size_t)scan_pos(j) * cols) = (uint16_t)(ca | (cb << 8));
-  }
+// Quantise + map + store the 64 lane pairs of one channel, visiting the planes in scan order so
+// that the store address is a running pointer (+cols).  `rec` points at the channel's class.
+template <int I>
+__device__ __forceinline__ void quant_one(const uint32_t (&x)[64], const QuantRec *rec, const uint8_t *slut,
+                                          uint8_t *&dst, int cols) {
+  constexpr int j = scan_coef(I);
+  const uint4 k = *reinterpret_cast<const uint4 *>(&rec[I]);  // c2, tmask, smask, off2 (broadcast)
+  const uint32_t sh = rec[I].shift;
+  // lane = T + 16384.  Sign-magnitude rounding: (T + r - [T < 0]) >> s, and [T >= 0] is bit 14.
+  const uint32_t z = x[j];
+  const uint32_t tz = (z >> 14) & k.y;
+  const uint32_t m = (((z + k.x + tz) >> sh) & k.z) + k.w;
+  const uint32_t ca = slut[m & 0xffffu], cb = slut[m >> 16];
+  *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(ca | (cb << 8));
+  dst += cols;
+}
+template <int... Is>
+__device__ __forceinline__ void quant_store(const uint32_t (&x)[64], const QuantRec *rec, const uint8_t *slut,
+                                            uint8_t *dst, int cols, std::integer_sequence<int, Is...>) {
+  (quant_one<Is>(x, rec, slut, dst, cols), ...);
 }
 
-// grid (ceil(cols/256), rows, n), block 128, dynamic smem 8 * 256*8*NCH bytes.
+// grid (ceil(cols/tile_cols), ceil(rows/tile_rows), n), block 256.
+// dynamic smem: tile (tile_rows*8 pixel rows of tile_cols*8*NCH bytes) | quantiser records | LUT.
+// The 8 warps of a CTA pass through the phases together (barriers at the phase boundaries): with
+// 2 CTAs per SM the live instruction window stays inside the instruction cache.
 template <int NCH, bool YCBCR>
-__global__ void __launch_bounds__(kFwd2Threads, 4)
+__global__ void __launch_bounds__(kFwd2Threads, 2)
     k_forward2(const uint8_t *__restrict__ pixels, const uint8_t *__restrict__ L, Geom g,
-               const __grid_constant__ Fwd2Params prm, const uint8_t *__restrict__ slut,
-               uint8_t *__restrict__ planes) {
+               const __grid_constant__ Fwd2Params prm, const QuantPacked *__restrict__ qrecs,
+               const uint8_t *__restrict__ slut, uint8_t *__restrict__ planes) {
   extern __shared__ __align__(128) uint8_t tile[];
   __shared__ uint64_t bar;
-  constexpr int kRowPitch = kFwd2Blocks * 8 * NCH;
-  uint8_t *lut = tile + 8 * kRowPitch;  // signed map LUT, 2*lut_half + 1 bytes
-  const int v = blockIdx.y, u0 = blockIdx.x * kFwd2Blocks;
-  const int nblk = min(kFwd2Blocks, g.cols - u0);  // even
+  const int pitch = prm.tile_cols * 8 * NCH;  // bytes per staged pixel row (multiple of 16)
+  const int v0 = blockIdx.y * prm.tile_rows, u0 = blockIdx.x * prm.tile_cols;
+  const int nblk = min(prm.tile_cols, g.cols - u0);  // even
+  const int nrow = min(prm.tile_rows, g.rows - v0);
+  QuantRec *recs = reinterpret_cast<QuantRec *>(tile + (size_t)prm.tile_rows * 8 * pitch);
+  uint8_t *lut = reinterpret_cast<uint8_t *>(recs + 128);  // signed map LUT, 2*lut_half + 1 bytes
+  // low-res samples needed by the tile: [NCH][tile_rows + 1][tile_cols + 2], edge clamped
+  const int lw = prm.tile_cols + 2, lh = prm.tile_rows + 1;
+  uint8_t *sL = lut + ((2 * prm.lut_half + 1 + 15) & ~15);
   const uint8_t *img = pixels + (size_t)blockIdx.z * g.img_bytes;
 
   if (threadIdx.x == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     const uint32_t row_bytes = (uint32_t)nblk * 8 * NCH;
-    mbar_expect_tx(&bar, row_bytes * 8);
-#pragma unroll
-    for (int y = 0; y < 8; ++y)
-      bulk_g2s(tile + y * kRowPitch, img + ((size_t)(8 * v + y) * g.w + (size_t)u0 * 8) * NCH, row_bytes, &bar);
+    mbar_expect_tx(&bar, row_bytes * 8 * nrow);
+    for (int y = 0; y < 8 * nrow; ++y)
+      bulk_g2s(tile + y * pitch, img + ((size_t)(8 * v0 + y) * g.w + (size_t)u0 * 8) * NCH, row_bytes, &bar);
   }
-  {  // copy the needed window of the signed LUT while the tile is in flight
-    const int half = prm.q.lut_half, nw = (2 * half + 1 + 3) >> 2;
-    const uint8_t *src = slut + (kLutCenter - half);
-    for (int i = threadIdx.x; i < nw; i += kFwd2Threads) {
-      uint32_t wv = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) wv |= (uint32_t)__ldg(src + min(4 * i + b, 2 * half)) << (8 * b);
-      reinterpret_cast<uint32_t *>(lut)[i] = wv;
+  {  // quantiser records and the needed window of the signed LUT, while the tile is in flight
+    const uint4 *qs = reinterpret_cast<const uint4 *>(qrecs);
+    for (int i = threadIdx.x; i < (int)(sizeof(QuantPacked) / 16); i += kFwd2Threads)
+      reinterpret_cast<uint4 *>(recs)[i] = __ldg(qs + i);
+    // lut_half is a multiple of 64 and the global table is padded: aligned 128-bit copies
+    const int half = prm.lut_half, nv = (2 * half + 1 + 15) >> 4;
+    const uint4 *src = reinterpret_cast<const uint4 *>(slut + (kLutCenter - half));
+    for (int i = threadIdx.x; i < nv; i += kFwd2Threads) reinterpret_cast<uint4 *>(lut)[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < NCH * lh * lw; i += kFwd2Threads) {
+      const int c = i / (lh * lw), r = (i - c * lh * lw) / lw, q = i - c * lh * lw - r * lw;
+      const int vv = min(v0 + r, g.rows - 1), uu = min(u0 + q, g.cols - 1);
+      sL[i] = __ldg(L + (((size_t)blockIdx.z * NCH + c) * g.rows + vv) * g.cols + uu);
     }
   }
   __syncthreads();
-  const int ub = 2 * threadIdx.x;  // first of this thread's two blocks, tile relative
-  const bool active = ub < nblk;
-  const int u = u0 + ub;
+  const int half_cols = prm.tile_cols >> 1;
+  const int rb = threadIdx.x / half_cols;               // block row inside the tile
+  const int ub = 2 * (threadIdx.x - rb * half_cols);    // first of this thread's two blocks
+  const bool active = rb < nrow && ub < nblk;
+  const int v = v0 + rb, u = u0 + ub;
   uint8_t *seg = planes + (size_t)blockIdx.z * g.planes_bytes + (size_t)v * g.seg + u;
+  const uint8_t *trow = tile + (size_t)rb * 8 * pitch + ub * 8 * NCH;
   mbar_wait(&bar, 0);
-  if (!active) return;
 
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     uint32_t x[64];
-    int cw0[4], cw1[4];
+    __syncthreads();  // keep the CTA's warps in the same phase (instruction-cache locality)
+    if (active) {
+      int cw0[4], cw1[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      cw0[k] = prm.cw[c].w0[k];
-      cw1[k] = prm.cw[c].w1[k];
-    }
-    const int cadd = prm.cw[c].add, cshr = prm.cw[c].shr;
-    // ---- low-res corners of both blocks (columns u, u+1, u+2; rows v, v+1), packed per lane
-    uint32_t lf[9], rt[9];
-    {
-      const uint8_t *Lc = L + ((size_t)blockIdx.z * NCH + c) * g.rows * g.cols;
-      const int v2 = min(v + 1, g.rows - 1), ua = u, ubb = min(u + 1, g.cols - 1), uc = min(u + 2, g.cols - 1);
-      const uint32_t t0 = __ldg(Lc + v * g.cols + ua), t1 = __ldg(Lc + v * g.cols + ubb), t2 = __ldg(Lc + v * g.cols + uc);
-      const uint32_t b0 = __ldg(Lc + v2 * g.cols + ua), b1 = __ldg(Lc + v2 * g.cols + ubb), b2 = __ldg(Lc + v2 * g.cols + uc);
-      nine2(t0 | (t1 << 16), b0 | (b1 << 16), lf);  // left columns of A (lo) and B (hi)
-      nine2(t1 | (t2 << 16), b1 | (b2 << 16), rt);  // right columns
-    }
-    // ---- rows: colour map, subtract the interpolated low-res row (bias 256), row WHT
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      const uint4 *rp = reinterpret_cast<const uint4 *>(tile + y * kRowPitch + ub * 8 * NCH);
-      uint32_t w[4 * NCH];  // block A words then block B words
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        const uint4 q = rp[k];
-        w[4 * k] = q.x;
-        w[4 * k + 1] = q.y;
-        w[4 * k + 2] = q.z;
-        w[4 * k + 3] = q.w;
+      for (int k = 0; k < 4; ++k) {
+        cw0[k] = prm.cw[c].w0[k];
+        cw1[k] = prm.cw[c].w1[k];
       }
-      uint32_t t[9];
-      nine2(lf[y], rt[y], t);
-      const uint32_t *wa = w, *wb = w + 2 * NCH;
+      const int cadd = prm.cw[c].add, cshr = prm.cw[c].shr;
+      // ---- low-res corners of both blocks (columns u, u+1, u+2; rows v, v+1), packed per lane
+      uint32_t lf[9], rt[9];
+      {
+        const uint8_t *lp = sL + (c * lh + rb) * lw + ub;  // clamping was applied when staging
+        const uint32_t t0 = lp[0], t1 = lp[1], t2 = lp[2];
+        const uint32_t b0 = lp[lw], b1 = lp[lw + 1], b2 = lp[lw + 2];
+        nine2(t0 | (t1 << 16), b0 | (b1 << 16), lf);  // left columns of A (lo) and B (hi)
+        nine2(t1 | (t2 << 16), b1 | (b2 << 16), rt);  // right columns
+      }
+      // ---- rows: colour map, subtract the interpolated low-res row (bias 256), row WHT
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[y * 8 + i] = colour_pair<NCH>(wa, wb, i, cw0, cw1, cadd, cshr) - t[i] + 0x01000100u;
-      wht8p<256>(x[y * 8 + 0], x[y * 8 + 1], x[y * 8 + 2], x[y * 8 + 3], x[y * 8 + 4], x[y * 8 + 5], x[y * 8 + 6], x[y * 8 + 7]);
+      for (int y = 0; y < 8; ++y) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(trow + y * pitch);
+        uint32_t w[4 * NCH];  // block A words then block B words
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const uint4 q = rp[k];
+          w[4 * k] = q.x;
+          w[4 * k + 1] = q.y;
+          w[4 * k + 2] = q.z;
+          w[4 * k + 3] = q.w;
+        }
+        uint32_t t[9];
+        nine2(lf[y], rt[y], t);
+        const uint32_t *wa = w, *wb = w + 2 * NCH;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[y * 8 + i] = colour_pair<NCH>(wa, wb, i, cw0, cw1, cadd, cshr) - t[i] + 0x01000100u;
+        wht8p<256>(x[y * 8 + 0], x[y * 8 + 1], x[y * 8 + 2], x[y * 8 + 3], x[y * 8 + 4], x[y * 8 + 5], x[y * 8 + 6], x[y * 8 + 7]);
+      }
+      // ---- columns (bias 2048 -> 16384)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        wht8p<2048>(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
     }
-    // ---- columns (bias 2048 -> 16384)
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      wht8p<2048>(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
+    __syncthreads();
     // ---- quantise both lanes, map, store the code pair
-    uint8_t *dst = seg + (size_t)c * g.cols * 64;
-    if (YCBCR && NCH >= 3 && (c == 1 || c == 2)) quant_store<1>(x, prm.q, lut, dst, g.cols);
-    else quant_store<0>(x, prm.q, lut, dst, g.cols);
+    if (active) {
+      const int cls = (YCBCR && NCH >= 3 && (c == 1 || c == 2)) ? 1 : 0;
+      quant_store(x, recs + cls * 64, lut, seg + (size_t)c * g.cols * 64, g.cols, std::make_integer_sequence<int, 64>{});
+    }
   }
 }
 
