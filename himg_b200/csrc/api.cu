@@ -588,10 +588,11 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
          d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
          d_status);
-  LAUNCH("k_dec_stream_lres", k_dec_stream, dim3(1, n), kDecThreads, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
+  // one CTA per stream: the single LRES stream of an image gets a wide team, a block row a warp
+  LAUNCH("k_dec_stream_lres", k_dec_stream_par, dim3(1, n), kParLresThreads, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
          g.lres_size, d_lres, g.lres_stride, d_status);
-  LAUNCH("k_dec_stream_fres", k_dec_stream, dim3((g.rows + kDecThreads - 1) / kDecThreads, n), kDecThreads, 0,
-         d_himg, d_fcd, d_ftree, d_fseg, g.rows, g.seg, d_planes, g.planes_bytes, d_status);
+  LAUNCH("k_dec_stream_fres", k_dec_stream_par, dim3(g.rows, n), kParFresThreads, 0, d_himg, d_fcd, d_ftree, d_fseg,
+         g.rows, g.seg, d_planes, g.planes_bytes, d_status);
   const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
   const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
   LAUNCH("k_lres_dpcm_dec", (k_lres_dpcm<false>), blocks, kLresWarps * 32, 0, (const uint8_t *)nullptr, d_lres, d_R,
@@ -988,7 +989,7 @@ int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in
   LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_in, d_cd, lenient, d_tree, d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_in, d_cd, d_tree, n, nseg, seg, whole ? 0 : 1, lenient, d_seg,
          d_status);
-  LAUNCH("k_dec_stream", k_dec_stream, dim3((nseg + kDecThreads - 1) / kDecThreads, n), kDecThreads, 0, d_in, d_cd,
+  LAUNCH("k_dec_stream", k_dec_stream_par, dim3(nseg, n), nseg == 1 ? kParLresThreads : kParFresThreads, 0, d_in, d_cd,
          d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);
   return HIMGCU_OK;
 }

@@ -17,14 +17,35 @@ namespace himgcu {
 constexpr int kLutBits = 10;
 constexpr int kLutSize = 1 << kLutBits;
 
+// Decode LUT entry (indexed by the next 10 stream bits, LSB first):
+//   bits 0-7   literal byte (0 for zero-run tokens)
+//   bits 8-12  code length in bits (0 only for a single-leaf tree in strict mode)
+//   bits 13-16 number of extra bits that follow the code (0, 2, 4, 8 or 14)
+//   bits 17-25 run base: output bytes = base + extra  (1 for literals)
+//   bit 30     invalid slot (incomplete tree or symbol > 260)
+//   bit 31     code longer than 10 bits: bits 0-15 hold the tree node reached after 10 bits
+constexpr uint32_t kLutLong = 0x80000000u, kLutInvalid = 0x40000000u;
+
+__host__ __device__ inline uint32_t lut_entry(int sym, int len) {
+  if (sym > 260) return kLutInvalid;
+  uint32_t lit = 0, nx = 0, base = 1;
+  if (sym <= 255) lit = (uint32_t)sym;
+  else if (sym == 256) base = 2;
+  else if (sym == 257) nx = 2, base = 3;
+  else if (sym == 258) nx = 4, base = 7;
+  else if (sym == 259) nx = 8, base = 23;
+  else nx = 14, base = 279;
+  return lit | ((uint32_t)len << 8) | (nx << 13) | (base << 17);
+}
+
 struct ChunkDesc {
   unsigned long long off;  // byte offset of the chunk payload inside the data buffer
   uint32_t size;
   uint32_t ok;
 };
 
-struct DecTree {
-  uint32_t lut[kLutSize];  // leaf: sym | len << 16;  long code: 0x80000000 | node at depth 10
+struct __align__(16) DecTree {
+  uint32_t lut[kLutSize];  // see lut_entry()
   short ca[kMaxNodes], cb[kMaxNodes], sym[kMaxNodes];
   short pad;
   int nnodes;
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(kDecTreeThreads)
   const ChunkDesc d = cd[item];
   const int avail = d.ok ? (int)min((uint32_t)kTreeBytesMax, d.size) : 0;
   for (int i = t; i < kTreeBytesMax + 8; i += blockDim.x) raw[i] = i < avail ? data[d.off + i] : 0;
-  for (int i = t; i < kLutSize; i += blockDim.x) out->lut[i] = 0;  // len 0 / sym 0: never advances
+  for (int i = t; i < kLutSize; i += blockDim.x) out->lut[i] = kLutInvalid;
   __syncthreads();
   if (t == 0) {
     int n = 0, ok = d.ok ? 1 : 0, sp = 0, bit = 0;
@@ -239,11 +260,11 @@ __global__ void __launch_bounds__(kDecTreeThreads)
         // The reference's decoder consumes ZERO bits per symbol for a single-leaf tree
         // (huffman_dec.cpp:178-188) although its encoder wrote one; lenient mode consumes it.
         const uint32_t len = (single && lenient) ? 1u : (uint32_t)dep;
-        const uint32_t e = (uint32_t)nsym[k] | (len << 16);
+        const uint32_t e = lut_entry(nsym[k], (int)len);
         for (uint32_t i = 0; i < (1u << (kLutBits - dep)); ++i) out->lut[(i << dep) | pcode[k]] = e;
       }
     } else if (dep == kLutBits) {
-      out->lut[pcode[k]] = 0x80000000u | (uint32_t)k;
+      out->lut[pcode[k]] = kLutLong | (uint32_t)k;
     }
   }
   if (t == 0) {
@@ -321,33 +342,42 @@ __global__ void k_dec_segtab(const uint8_t *__restrict__ data, const ChunkDesc *
   }
 }
 
-// ---- stream decode (huffman_dec.cpp:274-418) ---------------------------------------------------
-struct BitReader {
-  const uint8_t *p;
-  uint32_t nbytes, rd;
+// ---- subsequence-parallel stream decode ---------------------------------------------------------
+// A team of threads (one CTA) decodes ONE stream.  The bit stream is cut into equal subsequences;
+// thread t starts decoding at a guessed position (the subsequence boundary, usually in the middle
+// of a code word).  Huffman codes self-synchronise: after a few symbols a wrongly started decoder
+// falls onto true code-word boundaries.  Rounds of "take the end position of the previous thread
+// as my start" are repeated until nothing changes (thread 0 is right from the start, so round r
+// fixes at least thread r; in practice 2-3 rounds).  Output offsets are a prefix sum of the
+// per-thread byte counts, then every thread decodes its subsequence once more and writes.
+struct PBits {
+  const uint32_t *w;  // 4-byte aligned base at or below the stream start
+  int last_word;      // last word index that holds a valid byte (-1: empty stream)
+  uint32_t widx;
+  uint32_t nxt;       // word widx, fetched one refill ahead so the load latency is off the critical path
   uint64_t buf;
   int nb;
-  uint32_t pos;  // bits consumed
-  __device__ __forceinline__ void init(const uint8_t *ptr, uint32_t n) {
-    p = ptr;
-    nbytes = n;
-    rd = 0;
-    buf = 0;
-    nb = 0;
-    pos = 0;
-    while (rd < nbytes && ((reinterpret_cast<uintptr_t>(p + rd)) & 3)) {
-      buf |= (uint64_t)p[rd] << nb;
-      nb += 8;
-      ++rd;
-    }
+  uint32_t pos;  // stream-relative bit position of buf bit 0
+  __device__ __forceinline__ uint32_t ld(uint32_t i) const { return (int)i <= last_word ? __ldg(w + i) : 0u; }
+  __device__ __forceinline__ void seek(const uint8_t *base, uint32_t nbytes, uint32_t bitpos) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+    const uint32_t boff = (uint32_t)(a & 3) * 8;
+    w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    last_word = nbytes ? (int)((boff + 8 * nbytes - 1) >> 5) : -1;
+    const uint32_t ap = boff + bitpos;
+    widx = ap >> 5;
+    const uint32_t w0 = ld(widx), w1 = ld(widx + 1);
+    widx += 2;
+    nxt = ld(widx);
+    buf = (((uint64_t)w1 << 32) | w0) >> (ap & 31);
+    nb = 64 - (int)(ap & 31);
+    pos = bitpos;
   }
   __device__ __forceinline__ void refill() {
-    // aligned 32-bit loads; a word is fetched only if it holds at least one valid byte
-    if (nb <= 32 && rd < nbytes) {
-      const uint32_t w = *reinterpret_cast<const uint32_t *>(p + rd);
-      buf |= (uint64_t)w << nb;
+    if (nb <= 32) {
+      buf |= (uint64_t)nxt << nb;
       nb += 32;
-      rd += 4;
+      nxt = ld(++widx);
     }
   }
   __device__ __forceinline__ void consume(int n) {
@@ -357,116 +387,202 @@ struct BitReader {
   }
 };
 
-constexpr int kDecThreads = 32;
-
-// grid (ceil(nseg/32), n), block 32: one thread per segment.  Output segment b of item i goes to
-// out + i*out_stride + b*out_seg (out_seg bytes).
-__global__ void __launch_bounds__(kDecThreads)
-    k_dec_stream(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
-                 const DecTree *__restrict__ trees, const SegRef *__restrict__ segs, int nseg,
-                 int out_seg, uint8_t *__restrict__ out, unsigned long long out_stride,
-                 int *__restrict__ status) {
-  __shared__ uint32_t lut[kLutSize];
-  __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
-  const int item = blockIdx.y, b = blockIdx.x * kDecThreads + threadIdx.x;
-  const DecTree *T = trees + item;
-  for (int i = threadIdx.x; i < kLutSize; i += kDecThreads) lut[i] = T->lut[i];
-  const int nn = T->ok ? T->nnodes : 0;
-  for (int i = threadIdx.x; i < nn; i += kDecThreads) {
-    ca[i] = T->ca[i];
-    cb[i] = T->cb[i];
-    nsym[i] = T->sym[i];
+// Decodes one token.  Returns the number of output bytes it stands for (1 for a literal, the run
+// length for a zero-run token) or -1 on an invalid code; *lit receives the literal byte (0 for
+// runs).  After refill() at least 33 bits are buffered: enough for a 10-bit code + 14 extra bits.
+struct SNodes {
+  const short *ca, *cb, *sym;
+};
+__device__ __forceinline__ int decode_token(PBits &b, const uint32_t *lut, const SNodes &T, int *lit) {
+  b.refill();
+  uint32_t e = lut[(uint32_t)b.buf & (kLutSize - 1)];
+  if (e & (kLutLong | kLutInvalid)) {
+    if (e & kLutInvalid) return -1;
+    int node = (int)(e & 0xffffu), sym, guard = 0;
+    b.consume(kLutBits);
+    for (;;) {
+      sym = T.sym[node];
+      if (sym >= 0) break;
+      b.refill();
+      const int bit = (int)(b.buf & 1u);
+      b.consume(1);
+      node = bit ? T.cb[node] : T.ca[node];
+      if (node < 0 || ++guard > kMaxNodes) return -1;
+    }
+    e = lut_entry(sym, 0);
+    if (e & kLutInvalid) return -1;
+    b.refill();
   }
-  __syncwarp();
-  if (b >= nseg) return;
+  b.consume((int)((e >> 8) & 31u));
+  const int nx = (int)((e >> 13) & 15u);
+  const int z = (int)((e >> 17) & 511u) + (int)((uint32_t)b.buf & ((1u << nx) - 1u));
+  b.consume(nx);
+  *lit = (int)(e & 255u);
+  return z;
+}
+
+constexpr uint32_t kPosInvalid = 0xffffffffu;
+constexpr int kParFresThreads = 32;   // team per block-row segment
+constexpr int kParLresThreads = 256;  // team for the single unframed LRES stream
+constexpr int kParMaxTeam = 256;
+
+// grid (nseg, n), block TEAM (multiple of 32, <= 1024): one CTA per stream.
+__global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
+                                 const DecTree *__restrict__ trees, const SegRef *__restrict__ segs, int nseg,
+                                 int out_seg, uint8_t *__restrict__ out, unsigned long long out_stride,
+                                 int *__restrict__ status) {
+  __shared__ __align__(16) uint32_t lut[kLutSize];
+  __shared__ __align__(16) short s_nodes[3 * (kMaxNodes + 3)];
+  __shared__ uint32_t s_end[kParMaxTeam];
+  __shared__ uint32_t ws[33];
+  __shared__ int s_changed, s_bad, s_final;
+  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x, team = blockDim.x;
+  const DecTree *T = trees + item;
   const SegRef sr = segs[(size_t)item * nseg + b];
-  if (!T->ok || sr.size == 0xffffffffu) {
-    atomicMax(&status[item], 1);
+  if (!T->ok || sr.size == 0xffffffffu || sr.size == 0) {  // an empty stream cannot produce out_seg > 0 bytes
+    if (t == 0) atomicMax(&status[item], 1);
     return;
   }
+  {
+    const uint4 *ls = reinterpret_cast<const uint4 *>(T->lut);
+#pragma unroll 4
+    for (int i = t; i < kLutSize / 4; i += team) reinterpret_cast<uint4 *>(lut)[i] = __ldg(ls + i);
+    const int nn = T->nnodes;
+    for (int i = t; i < nn; i += team) {
+      s_nodes[i] = T->ca[i];
+      s_nodes[(kMaxNodes + 3) + i] = T->cb[i];
+      s_nodes[2 * (kMaxNodes + 3) + i] = T->sym[i];
+    }
+  }
+  const SNodes SN{s_nodes, s_nodes + (kMaxNodes + 3), s_nodes + 2 * (kMaxNodes + 3)};
+  if (t == 0) s_bad = 0, s_final = -1;
+  __syncthreads();
+  const uint8_t *src = data + cd[item].off + sr.off;
   uint8_t *o = out + (size_t)item * out_stride + (size_t)b * out_seg;
-  uint32_t *ow = reinterpret_cast<uint32_t *>(o);  // segment bases are 4-byte aligned
-  BitReader br;
-  br.init(data + cd[item].off + sr.off, sr.size);
   const uint32_t total_bits = sr.size * 8u;
-  int n = 0;
-  uint32_t acc = 0;
-  bool ok = true;
-  while (n < out_seg) {
-    br.refill();
-    const uint32_t e = lut[(uint32_t)br.buf & (kLutSize - 1)];
-    int sym;
-    if (!(e & 0x80000000u)) {
-      sym = (int)(e & 0xffffu);
-      br.consume((int)(e >> 16));
+
+  // The segment is zero-filled cooperatively (coalesced stores); the write pass then only stores
+  // the non-zero literals -- three out of four coefficient bytes are zeros at quality 50.
+  {
+    const bool al16 = ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)out_seg) & 15) == 0;
+    if (al16) {
+      for (int i = t; i < (out_seg >> 4); i += team) reinterpret_cast<uint4 *>(o)[i] = make_uint4(0, 0, 0, 0);
     } else {
-      int node = (int)(e & 0xffffu);
-      br.consume(kLutBits);
-      while (nsym[node] < 0 && br.pos <= total_bits) {
-        br.refill();
-        const int bit = (int)(br.buf & 1u);
-        br.consume(1);
-        node = bit ? cb[node] : ca[node];
-      }
-      sym = nsym[node];
+      for (int i = t; i < out_seg; i += team) o[i] = 0;
     }
-    if (br.pos > total_bits || sym < 0) {
-      ok = false;
-      break;
-    }
-    if (sym <= 255) {
-      acc |= (uint32_t)sym << (8 * (n & 3));
-      ++n;
-      if ((n & 3) == 0) {
-        ow[(n >> 2) - 1] = acc;
-        acc = 0;
-      }
-    } else {
-      int z;
-      if (sym == 256) {
-        z = 2;
-      } else {
-        const int nx = sym == 257 ? 2 : (sym == 258 ? 4 : (sym == 259 ? 8 : 14));
-        const int addv = sym == 257 ? 3 : (sym == 258 ? 7 : (sym == 259 ? 23 : 279));
-        if (sym > 260) {
+  }
+  __syncthreads();
+
+  if (T->single) {
+    // Single-leaf tree: every token has the same code (0 bits for the reference decoder, 1 bit in
+    // lenient mode, see k_dec_tree); nothing to parallelise.
+    if (t == 0) {
+      PBits br;
+      br.seek(src, sr.size, 0);
+      int n = 0;
+      bool ok = true;
+      while (n < out_seg) {
+        int lit;
+        const int z = decode_token(br, lut, SN, &lit);
+        if (z < 0 || br.pos > total_bits || n + z > out_seg) {
           ok = false;
           break;
         }
-        br.refill();
-        z = (int)((uint32_t)br.buf & ((1u << nx) - 1u)) + addv;
-        br.consume(nx);
-        if (br.pos > total_bits) {
+        if (lit) o[n] = (uint8_t)lit;
+        n += z;
+      }
+      if (ok) ok = br.pos > 8u * (sr.size - 1) && br.pos <= total_bits;
+      if (!ok) atomicMax(&status[item], 1);
+    }
+    return;
+  }
+
+  // ---- phase 1: synchronise.  Thread t owns the tokens that START in [start_t, end_t).
+  uint32_t sub = (total_bits + team - 1) / team;
+  sub = max((sub + 31u) & ~31u, 128u);
+  const uint32_t bound_lo = min((uint32_t)t * sub, total_bits);        // nominal start
+  const uint32_t bound_hi = min((uint32_t)(t + 1) * sub, total_bits);  // tokens starting here belong to t+1
+  const bool has_work = bound_lo < total_bits;
+  uint32_t start = bound_lo, endpos = kPosInvalid, count = 0;
+  bool dirty = has_work;
+  for (int round = 0; round <= team; ++round) {
+    if (dirty) {
+      PBits br;
+      br.seek(src, sr.size, start);
+      count = 0;
+      endpos = kPosInvalid;
+      bool ok = true;
+      while (br.pos < bound_hi) {
+        int lit;
+        const int z = decode_token(br, lut, SN, &lit);
+        if (z < 0 || br.pos > total_bits) {
           ok = false;
           break;
         }
+        count += (uint32_t)z;
       }
-      if (n + z > out_seg) {
-        ok = false;
+      // the last subsequence may run into the (possibly non-zero) padding bits: that is not an error
+      if (ok) endpos = br.pos;
+      else if (bound_hi == total_bits) endpos = total_bits;
+    }
+    s_end[t] = has_work ? endpos : kPosInvalid;
+    if (t == 0) s_changed = 0;
+    __syncthreads();
+    dirty = false;
+    if (has_work && t > 0) {
+      const uint32_t prev = s_end[t - 1];
+      // a start beyond my own range means the previous thread's token swallowed my subsequence
+      if (prev != kPosInvalid && prev != start) {
+        start = prev;
+        dirty = start < bound_hi || bound_hi == total_bits;
+        if (!dirty) {
+          count = 0;
+          endpos = start;  // nothing starts in my range: pass the position through
+        }
+        s_changed = 1;
+      }
+    }
+    __syncthreads();
+    if (!s_changed) break;
+    __syncthreads();
+  }
+
+  // ---- output offsets
+  uint32_t total;
+  const uint32_t off = block_exscan_u32(has_work ? count : 0u, ws, &total);
+  // threads whose output lies inside the segment must have decoded cleanly
+  if (has_work && off < (uint32_t)out_seg && endpos == kPosInvalid) s_bad = 1;
+  __syncthreads();
+  if (s_bad) {
+    if (t == 0) atomicMax(&status[item], 1);
+    return;
+  }
+
+  // ---- phase 2: decode again and write the non-zero literals
+  if (has_work && off < (uint32_t)out_seg && start < total_bits) {
+    PBits br;
+    br.seek(src, sr.size, start);
+    int n = (int)off;
+    bool ok = true;
+    while (br.pos < bound_hi && n < out_seg) {
+      int lit;
+      const int z = decode_token(br, lut, SN, &lit);
+      if (z < 0 || br.pos > total_bits || n + z > out_seg) {
+        ok = false;  // a zero run that overshoots the segment is an error (huffman_dec.cpp:352)
         break;
       }
-      while (z && (n & 3)) {
-        ++n;
-        --z;
-        if ((n & 3) == 0) {
-          ow[(n >> 2) - 1] = acc;
-          acc = 0;
-        }
-      }
-      while (z >= 4) {
-        ow[n >> 2] = 0;
-        n += 4;
-        z -= 4;
-      }
-      n += z;  // acc stays 0, the tail is flushed with the next bytes
+      if (lit) o[n] = (uint8_t)lit;
+      n += z;
+      if (n == out_seg) s_final = (int)br.pos;
     }
+    if (!ok) s_bad = 1;
   }
-  if (ok && (n & 3)) {
-    for (int k = 0; k < (n & 3); ++k) o[(n & ~3) + k] = (uint8_t)(acc >> (8 * k));
+  __syncthreads();
+  if (t == 0) {
+    // complete output, and the read position inside the last byte (BitStream::AtTheEnd)
+    const bool ok = !s_bad && s_final >= 0 && (uint32_t)s_final > 8u * (sr.size - 1) && (uint32_t)s_final <= total_bits;
+    if (!ok) atomicMax(&status[item], 1);
   }
-  // BitStream::AtTheEnd (huffman_dec.cpp:140-145): the read position must be inside the last byte
-  // or exactly at the end.
-  if (ok) ok = sr.size == 0 ? br.pos == 0 : (br.pos > 8u * (sr.size - 1) && br.pos <= total_bits);
-  if (!ok) atomicMax(&status[item], 1);
 }
 
 }  // namespace himgcu
