@@ -588,7 +588,9 @@ __global__ void __launch_bounds__(kHuffThreads)
         c1 = win[kWinWords + 1];
       }
       __syncthreads();
-      for (int i = t; i < kWinWords + 2; i += blockDim.x) win[i] = i == 0 ? c0 : (i == 1 ? c1 : 0u);
+      // only the words this window touched need clearing
+      const int used = last_win ? (int)((vend - w0 + 31) >> 5) + 3 : kWinWords + 2;
+      for (int i = t; i < min(used, kWinWords + 2); i += blockDim.x) win[i] = i == 0 ? c0 : (i == 1 ? c1 : 0u);
       __syncthreads();
       if (last_win) break;
     }
