@@ -15,6 +15,7 @@
 #include "huff_enc_kernels.cuh"
 #include "tables.h"
 #include "xform_fwd2.cuh"
+#include "xform_inv2.cuh"
 #include "xform_kernels.cuh"
 
 using namespace himgcu;
@@ -423,8 +424,32 @@ int launch_inv(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int
   return HIMGCU_OK;
 }
 
+template <int NCH>
+int launch_inv2(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
+                const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  // balanced column tiles of at most 256 blocks, multiples of 16 blocks
+  const int nt = (g.cols + kInv2Pitch - 1) / kInv2Pitch;
+  const int tile_cols = std::min(kInv2Pitch, (((g.cols + nt - 1) / nt) + 15) & ~15);
+  dim3 grid((g.cols + tile_cols - 1) / tile_cols, g.rows, n);
+  const int smem = NCH * 64 * kInv2Pitch + NCH * kInv2Threads * 17 * 4;
+  CK(cudaFuncSetAttribute(k_inverse2<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  LAUNCH("k_inverse", (k_inverse2<NCH>), grid, kInv2Threads, smem, d_planes, d_R, g, d_tabs, tab_stride, tile_cols,
+         d_pixels);
+  return HIMGCU_OK;
+}
+
 int stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
                   const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  if (!ctx->force_generic && (g.w % 8) == 0 && (g.h % 8) == 0 && (g.cols % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pixels) & 7) == 0 &&
+      (((size_t)g.w * g.nch) & 7) == 0) {
+    switch (g.nch) {
+      case 1: return launch_inv2<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+      case 3: return launch_inv2<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+      case 4: return launch_inv2<4>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+      default: break;
+    }
+  }
   switch (g.nch) {
     case 1: return launch_inv<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
     case 2: return launch_inv<2>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
