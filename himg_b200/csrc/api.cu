@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +40,8 @@ struct himgcu_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t in_stream = nullptr, out_stream = nullptr;  // copy streams of the host-buffer batch calls
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   std::string err;
   std::map<std::string, DevBuf> bufs;
   DevBuf full_lut;  // 7616-byte |x| -> code LUT, uploaded once
@@ -51,7 +55,7 @@ struct himgcu_ctx {
   std::vector<std::string> prof_names;
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
-  size_t host_sub_bytes = (size_t)4 << 30;
+  size_t host_sub_bytes = (size_t)192 << 20;  // staged bytes per sub-batch of the host-buffer calls
   bool force_generic = false;  // tests: route everything through the generic kernels
   // small table uploads are cached by key so that steady-state calls issue no host sync
   std::string qrec_key, lowres_key, prefix_key;  // device memory used per sub-batch of the host-buffer calls
@@ -625,6 +629,18 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   return stage_inverse(ctx, d_planes, d_R, n, g, d_tabs, sizeof(DecTables), d_pixels);
 }
 
+int ensure_pipeline(himgcu_ctx *ctx) {
+  if (ctx->in_stream) return HIMGCU_OK;
+  CK(cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    CK(cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_cmp[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
+  }
+  return HIMGCU_OK;
+}
+
 int ensure_pinned(himgcu_ctx *ctx, size_t bytes) {
   if (ctx->pinned_cap >= bytes) return HIMGCU_OK;
   if (ctx->pinned) {
@@ -679,6 +695,13 @@ void himgcu_destroy(himgcu_ctx *ctx) {
   if (ctx->signed_lut.p) cudaFree(ctx->signed_lut.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
+    if (ctx->ev_cmp[b]) cudaEventDestroy(ctx->ev_cmp[b]);
+    if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
+  }
+  if (ctx->in_stream) cudaStreamDestroy(ctx->in_stream);
+  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -869,41 +892,76 @@ void himgcu_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 
+// Host-buffer batches are pipelined: sub-batches flow through three streams (H2D, coding, D2H) with
+// double-buffered device staging, so the PCIe transfers of neighbouring sub-batches overlap the
+// kernels.  With pageable host memory the copies degrade to synchronous ones but stay correct.
 int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int w, int h, int nch, int quality,
                              int use_ycbcr, uint8_t *out, size_t out_cap, uint64_t *offsets, uint32_t *sizes) {
   if (!ctx || !pixels || !out || !offsets || !sizes || n < 0) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
   if (!shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", w, h, nch);
   CK(cudaSetDevice(ctx->device));
+  int rc = ensure_pipeline(ctx);
+  if (rc) return rc;
   const Geom g = make_geom(w, h, nch, nch);
   const bool ycbcr = use_ycbcr && nch >= 3;
   const size_t stride = (himgcu_encode_bound(w, h, nch) + 255) & ~(size_t)255;
-  const size_t per = per_image_encode_ws(g) + g.img_bytes + stride;
-  int sub = (int)std::min<size_t>((size_t)std::max(n, 1), std::max<size_t>(1, ctx->host_sub_bytes / per));
+  int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), ctx->host_sub_bytes / (g.img_bytes + stride)));
   sub = std::min(sub, 65535);
-  uint8_t *d_in, *d_out;
-  uint32_t *d_sizes;
-  ENSURE("hb_in", (size_t)sub * g.img_bytes, d_in);
-  ENSURE("hb_out", (size_t)sub * stride, d_out);
-  ENSURE("hb_sizes", (size_t)sub * sizeof(uint32_t), d_sizes);
+  const int K = (n + sub - 1) / sub;
+  uint8_t *d_in[2], *d_out[2];
+  uint32_t *d_sizes[2];
+  ENSURE("hb_in0", (size_t)sub * g.img_bytes, d_in[0]);
+  ENSURE("hb_in1", (size_t)sub * g.img_bytes, d_in[1]);
+  ENSURE("hb_out0", (size_t)sub * stride, d_out[0]);
+  ENSURE("hb_out1", (size_t)sub * stride, d_out[1]);
+  ENSURE("hb_sizes0", (size_t)sub * sizeof(uint32_t), d_sizes[0]);
+  ENSURE("hb_sizes1", (size_t)sub * sizeof(uint32_t), d_sizes[1]);
+  rc = ensure_pinned(ctx, 2 * (size_t)sub * sizeof(uint32_t));
+  if (rc) return rc;
+  uint32_t *h_sizes[2] = {reinterpret_cast<uint32_t *>(ctx->pinned), reinterpret_cast<uint32_t *>(ctx->pinned) + sub};
+  cudaStream_t s_in = ctx->in_stream, s_cmp = ctx->stream, s_out = ctx->out_stream;
+  CK(cudaStreamSynchronize(s_cmp));
+
+  auto issue = [&](int k) -> int {
+    const int b = k & 1, i0 = k * sub, m = std::min(sub, n - i0);
+    if (k >= 2) CK(cudaStreamWaitEvent(s_in, ctx->ev_cmp[b], 0));  // staging buffer consumed by sub-batch k-2
+    CK(cudaMemcpyAsync(d_in[b], pixels + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, s_in));
+    CK(cudaEventRecord(ctx->ev_in[b], s_in));
+    CK(cudaStreamWaitEvent(s_cmp, ctx->ev_in[b], 0));
+    if (k >= 2) CK(cudaStreamWaitEvent(s_cmp, ctx->ev_out[b], 0));  // output buffer drained
+    int r = encode_device(ctx, d_in[b], m, g, quality, ycbcr, d_out[b], stride, d_sizes[b]);
+    if (r) return r;
+    CK(cudaMemcpyAsync(h_sizes[b], d_sizes[b], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_cmp));
+    CK(cudaEventRecord(ctx->ev_cmp[b], s_cmp));
+    return HIMGCU_OK;
+  };
   uint64_t pos = 0;
   offsets[0] = 0;
-  for (int i0 = 0; i0 < n; i0 += sub) {
-    const int m = std::min(sub, n - i0);
-    CK(cudaMemcpyAsync(d_in, pixels + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = encode_device(ctx, d_in, m, g, quality, ycbcr, d_out, stride, d_sizes);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(sizes + i0, d_sizes, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+  const bool dbg = getenv("HIMG_DEBUG_PIPE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  for (int k = 0; k < std::min(K, 2); ++k)
+    if ((rc = issue(k))) return rc;
+  if (dbg) fprintf(stderr, "[pipe] K=%d sub=%d issued 2 at %.2f ms\n", K, sub, now() - t0);
+  for (int k = 0; k < K; ++k) {
+    const int b = k & 1, i0 = k * sub, m = std::min(sub, n - i0);
+    CK(cudaEventSynchronize(ctx->ev_cmp[b]));  // sizes of sub-batch k are on the host
+    if (dbg) fprintf(stderr, "[pipe] cmp %d done at %.2f ms\n", k, now() - t0);
     for (int i = 0; i < m; ++i) {
-      const uint32_t sz = sizes[i0 + i];
+      const uint32_t sz = h_sizes[b][i];
+      sizes[i0 + i] = sz;
       if (sz == 0) return fail(ctx, HIMGCU_ERR_CAPACITY, "image %d could not be encoded", i0 + i);
       if (pos + sz > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small");
-      CK(cudaMemcpyAsync(out + pos, d_out + (size_t)i * stride, sz, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(out + pos, d_out[b] + (size_t)i * stride, sz, cudaMemcpyDeviceToHost, s_out));
       pos += ((uint64_t)sz + 15) & ~15ull;
       offsets[i0 + i + 1] = pos;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_out[b], s_out));
+    if (k + 2 < K && (rc = issue(k + 2))) return rc;
   }
+  CK(cudaStreamSynchronize(s_out));
+  CK(cudaStreamSynchronize(s_cmp));
+  if (dbg) fprintf(stderr, "[pipe] all done at %.2f ms\n", now() - t0);
   return HIMGCU_OK;
 }
 
@@ -912,40 +970,62 @@ int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_
   if (!ctx || !himg || !offsets || !sizes || !pixels_out || !status || n < 0) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
   if (!shape_ok(w, h, nch)) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "unsupported shape %dx%dx%d", w, h, nch);
   CK(cudaSetDevice(ctx->device));
+  int rc = ensure_pipeline(ctx);
+  if (rc) return rc;
   const Geom g = make_geom(w, h, nch, nch);
-  const size_t stride = (himgcu_encode_bound(w, h, nch) + 255) & ~(size_t)255;
-  const size_t per = per_image_encode_ws(g) + g.out_img_bytes + stride;
-  int sub = (int)std::min<size_t>((size_t)std::max(n, 1), std::max<size_t>(1, ctx->host_sub_bytes / per));
+  int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), ctx->host_sub_bytes / (2 * g.out_img_bytes)));
   sub = std::min(sub, 65535);
-  uint8_t *d_px;
-  unsigned long long *d_off;
-  uint32_t *d_sz;
-  int *d_status;
-  ENSURE("hb_px", (size_t)sub * g.out_img_bytes, d_px);
-  ENSURE("hb_off", (size_t)sub * sizeof(unsigned long long), d_off);
-  ENSURE("hb_sz", (size_t)sub * sizeof(uint32_t), d_sz);
-  ENSURE("hb_status", (size_t)sub * sizeof(int), d_status);
-  std::vector<unsigned long long> rel(sub);
-  for (int i0 = 0; i0 < n; i0 += sub) {
-    const int m = std::min(sub, n - i0);
-    // the sub-batch's streams are copied as one contiguous host range
-    uint64_t lo = offsets[i0], hi = 0;
+  const int K = (n + sub - 1) / sub;
+  // contiguous host range of every sub-batch
+  std::vector<uint64_t> lo(K), hi(K);
+  size_t max_range = 0;
+  for (int k = 0; k < K; ++k) {
+    const int i0 = k * sub, m = std::min(sub, n - i0);
+    lo[k] = offsets[i0];
+    hi[k] = 0;
     for (int i = 0; i < m; ++i) {
-      lo = std::min<uint64_t>(lo, offsets[i0 + i]);
-      hi = std::max<uint64_t>(hi, offsets[i0 + i] + sizes[i0 + i]);
+      lo[k] = std::min<uint64_t>(lo[k], offsets[i0 + i]);
+      hi[k] = std::max<uint64_t>(hi[k], offsets[i0 + i] + sizes[i0 + i]);
     }
-    uint8_t *d_in;
-    ENSURE("hb_himg", (size_t)(hi - lo) + 64, d_in);
-    for (int i = 0; i < m; ++i) rel[i] = offsets[i0 + i] - lo;
-    CK(cudaMemcpyAsync(d_in, himg + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_off, rel.data(), (size_t)m * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_sz, sizes + i0, (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = decode_device(ctx, d_in, d_off, d_sz, m, g, flags, d_px, d_status);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(status + i0, d_status, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(pixels_out + (size_t)i0 * g.out_img_bytes, d_px, (size_t)m * g.out_img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // `rel` is reused by the next sub-batch
+    max_range = std::max<size_t>(max_range, (size_t)(hi[k] - lo[k]));
   }
+  uint8_t *d_px[2], *d_in[2];
+  unsigned long long *d_off[2];
+  uint32_t *d_sz[2];
+  int *d_status[2];
+  for (int b = 0; b < 2; ++b) {
+    const std::string sfx = std::to_string(b);
+    ENSURE(("hbd_px" + sfx).c_str(), (size_t)sub * g.out_img_bytes, d_px[b]);
+    ENSURE(("hbd_in" + sfx).c_str(), max_range + 64, d_in[b]);
+    ENSURE(("hbd_off" + sfx).c_str(), (size_t)sub * sizeof(unsigned long long), d_off[b]);
+    ENSURE(("hbd_sz" + sfx).c_str(), (size_t)sub * sizeof(uint32_t), d_sz[b]);
+    ENSURE(("hbd_status" + sfx).c_str(), (size_t)sub * sizeof(int), d_status[b]);
+  }
+  rc = ensure_pinned(ctx, (size_t)n * sizeof(unsigned long long));
+  if (rc) return rc;
+  unsigned long long *rel = reinterpret_cast<unsigned long long *>(ctx->pinned);  // stays valid until the end
+  cudaStream_t s_in = ctx->in_stream, s_cmp = ctx->stream, s_out = ctx->out_stream;
+  CK(cudaStreamSynchronize(s_cmp));
+  for (int k = 0; k < K; ++k) {
+    const int b = k & 1, i0 = k * sub, m = std::min(sub, n - i0);
+    for (int i = 0; i < m; ++i) rel[i0 + i] = offsets[i0 + i] - lo[k];
+    if (k >= 2) CK(cudaStreamWaitEvent(s_in, ctx->ev_cmp[b], 0));
+    CK(cudaMemcpyAsync(d_in[b], himg + lo[k], (size_t)(hi[k] - lo[k]), cudaMemcpyHostToDevice, s_in));
+    CK(cudaMemcpyAsync(d_off[b], rel + i0, (size_t)m * sizeof(unsigned long long), cudaMemcpyHostToDevice, s_in));
+    CK(cudaMemcpyAsync(d_sz[b], sizes + i0, (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice, s_in));
+    CK(cudaEventRecord(ctx->ev_in[b], s_in));
+    CK(cudaStreamWaitEvent(s_cmp, ctx->ev_in[b], 0));
+    if (k >= 2) CK(cudaStreamWaitEvent(s_cmp, ctx->ev_out[b], 0));
+    rc = decode_device(ctx, d_in[b], d_off[b], d_sz[b], m, g, flags, d_px[b], d_status[b]);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_cmp[b], s_cmp));
+    CK(cudaStreamWaitEvent(s_out, ctx->ev_cmp[b], 0));
+    CK(cudaMemcpyAsync(status + i0, d_status[b], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+    CK(cudaMemcpyAsync(pixels_out + (size_t)i0 * g.out_img_bytes, d_px[b], (size_t)m * g.out_img_bytes, cudaMemcpyDeviceToHost, s_out));
+    CK(cudaEventRecord(ctx->ev_out[b], s_out));
+  }
+  CK(cudaStreamSynchronize(s_out));
+  CK(cudaStreamSynchronize(s_cmp));
   return HIMGCU_OK;
 }
 

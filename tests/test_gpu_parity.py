@@ -429,3 +429,26 @@ def test_python_mirror_api(ctx, port):
     assert (dec.width(), dec.height(), dec.num_channels()) == (64, 48, 3)
     assert_same(dec.unpacked_data(), port.decode(enc.packed_data()), "mirror decode")
     assert not dec.Decode(b"nope", 4)
+
+
+def test_host_batch_api_pipelined(ctx, port):
+    """himgcu_encode_batch_host / himgcu_decode_batch_host: pinned and pageable host buffers, several
+    sub-batches in flight (forced by a small staging budget), ragged last sub-batch."""
+    w, h, n, B = 256, 136, 3, 11
+    imgs = np.stack([port.synth(w, h, n, 300 + k, 6) for k in range(B)])
+    want = [port.encode(imgs[k], 80, True) for k in range(B)]
+    ctx.set_option("host_sub_batch_bytes", 3 * (w * h * n + 2 * 1024 * 1024))  # ~3 images per sub-batch
+    try:
+        for pinned in (False, True):
+            src = torch.from_numpy(imgs).pin_memory() if pinned else imgs
+            out, offsets, sizes = ctx.encode_batch_host(src, 80, True)
+            out = np.asarray(out)
+            for k in range(B):
+                assert sizes[k] == len(want[k])
+                assert_same(out[int(offsets[k]): int(offsets[k]) + int(sizes[k])], np.frombuffer(want[k], np.uint8), f"host batch image {k}")
+            px, status = ctx.decode_batch_host(out, offsets, sizes, w, h, n)
+            assert int(np.abs(status).sum()) == 0
+            for k in range(B):
+                assert_same(px[k], port.decode(want[k]), f"host batch decode {k}")
+    finally:
+        ctx.set_option("host_sub_batch_bytes", 256 << 20)
