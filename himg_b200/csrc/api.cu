@@ -589,6 +589,14 @@ int encode_device(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g
   return huff_encode_items(ctx, n, ch, 2, true, d_out, out_stride, d_sizes);
 }
 
+// Threads per stream for k_dec_stream_par: grow the team until ~128k threads are in flight, but keep
+// at least ~256 output bytes per thread.
+int decode_team(long long streams, int out_bytes, int base) {
+  int team = base;
+  while (team < kParMaxTeam && streams * team < 131072 && out_bytes / (team * 2) >= 256) team *= 2;
+  return team;
+}
+
 // Whole-image decode of n streams resident on the device.
 int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long long *d_offsets,
                   const uint32_t *d_sizes, int n, const Geom &g, int flags, uint8_t *d_pixels, int *d_status) {
@@ -617,10 +625,13 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
          d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
          d_status);
-  // one CTA per stream: the single LRES stream of an image gets a wide team, a block row a warp
-  LAUNCH("k_dec_stream_lres", k_dec_stream_par, dim3(1, n), kParLresThreads, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
+  // one CTA per stream.  Team size: a warp per block row / 256 threads per LRES stream when the
+  // batch alone fills the GPU, wider teams when there are few streams (single images).
+  const int lres_team = decode_team(n, g.lres_size, kParLresThreads);
+  const int fres_team = decode_team((long long)n * g.rows, g.seg, kParFresThreads);
+  LAUNCH("k_dec_stream_lres", k_dec_stream_par, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
          g.lres_size, d_lres, g.lres_stride, d_status);
-  LAUNCH("k_dec_stream_fres", k_dec_stream_par, dim3(g.rows, n), kParFresThreads, 0, d_himg, d_fcd, d_ftree, d_fseg,
+  LAUNCH("k_dec_stream_fres", k_dec_stream_par, dim3(g.rows, n), fres_team, 0, d_himg, d_fcd, d_ftree, d_fseg,
          g.rows, g.seg, d_planes, g.planes_bytes, d_status);
   const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
   const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
@@ -1094,8 +1105,8 @@ int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in
   LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_in, d_cd, lenient, d_tree, d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_in, d_cd, d_tree, n, nseg, seg, whole ? 0 : 1, lenient, d_seg,
          d_status);
-  LAUNCH("k_dec_stream", k_dec_stream_par, dim3(nseg, n), nseg == 1 ? kParLresThreads : kParFresThreads, 0, d_in, d_cd,
-         d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);
+  LAUNCH("k_dec_stream", k_dec_stream_par, dim3(nseg, n), decode_team((long long)n * nseg, seg, nseg == 1 ? kParLresThreads : kParFresThreads),
+         0, d_in, d_cd, d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);
   return HIMGCU_OK;
 }
 

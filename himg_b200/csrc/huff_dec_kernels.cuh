@@ -424,7 +424,7 @@ __device__ __forceinline__ int decode_token(PBits &b, const uint32_t *lut, const
 constexpr uint32_t kPosInvalid = 0xffffffffu;
 constexpr int kParFresThreads = 32;   // team per block-row segment
 constexpr int kParLresThreads = 256;  // team for the single unframed LRES stream
-constexpr int kParMaxTeam = 256;
+constexpr int kParMaxTeam = 1024;
 
 // grid (nseg, n), block TEAM (multiple of 32, <= 1024): one CTA per stream.
 __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
