@@ -510,7 +510,8 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     ENSURE((tag + "_segbits").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_bits[k]);
     ENSURE((tag + "_segpos").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_pos[k]);
     dim3 grid(hg.nseg, n);
-    LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
+    if (ctx->force_generic) LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
+    else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
     LAUNCH("k_huff_tree", k_huff_tree, n, kTreeThreads, 0, d_seghist[k], hg.nseg, d_trees[k], d_err);
     LayoutChunk &C = P.ch[k];
     C.seghist = d_seghist[k];
@@ -534,8 +535,12 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   for (int k = 0; k < nchunks; ++k) {
     const HuffGeom &hg = chunks[k].hg;
     dim3 grid(hg.nseg, n);
-    LAUNCH("k_huff_pack", k_huff_pack, grid, kHuffThreads, win_bytes, chunks[k].d_in, hg, d_trees[k], d_bits[k],
-           d_pos[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
+    if (ctx->force_generic)
+      LAUNCH("k_huff_pack", k_huff_pack, grid, kHuffThreads, win_bytes, chunks[k].d_in, hg, d_trees[k], d_bits[k],
+             d_pos[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
+    else
+      LAUNCH("k_huff_pack", k_huff_pack2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_trees[k], d_bits[k], d_pos[k],
+             d_sizes, d_out, (unsigned long long)out_stride, d_err);
     if (hg.nseg > 1) {
       const long long tot = (long long)n * hg.nseg;
       LAUNCH("k_huff_stale", k_huff_stale, (unsigned)((tot + 255) / 256), 256, 0, n, hg.nseg, d_bits[k], d_pos[k],

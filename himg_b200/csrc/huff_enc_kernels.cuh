@@ -200,6 +200,101 @@ __global__ void __launch_bounds__(kHuffThreads)
   for (int i = threadIdx.x; i < kSyms; i += blockDim.x) dst[i] = sh[i];
 }
 
+// =================================================================================================
+// Balanced tokenisation (v2).  The walks above cost as much as the densest lane of a warp, and the
+// coefficient planes are very uneven (dense low frequencies, empty high frequencies).  Here the
+// non-zero bytes of a piece ("items") are first compacted into a position list in shared memory;
+// warps then take equal numbers of items.  Item k stands for [zero-run of gap_k bytes][literal]:
+// gap_0 = p_0 + zeros carried in, gap_k = p_k - p_(k-1) - 1.  The run that is still open at the end
+// of a piece is carried to the next piece; at the segment end it is emitted by one thread.
+// =================================================================================================
+constexpr int kTokThreads = 256;
+constexpr int kTokPiece = kTokThreads * kChunkBytes;  // 8 KiB
+constexpr int kTokWarps = kTokThreads / 32;
+
+struct PieceItems {
+  int count;        // number of items (non-zero bytes) in the piece
+  int len;          // valid bytes in the piece
+  uint32_t zeros_in;  // zeros carried in from earlier pieces
+};
+
+// Loads one piece, builds rows (for byte lookups) and the item position list.  Returns the zeros
+// carried out.  `ipos` holds kTokPiece u16, `ws` 9 words.  Ends with a barrier.
+__device__ __forceinline__ uint32_t build_items(const uint8_t *__restrict__ seg, int seg_size, int base, uint32_t *rows,
+                                                unsigned short *ipos, uint32_t *ws, uint32_t zeros_in, PieceItems *P) {
+  Chunk c;
+  load_chunk(c, rows, seg, seg_size, base + (int)threadIdx.x * kChunkBytes);
+  uint32_t total;
+  const uint32_t first = block_exscan_u32((uint32_t)__popc(c.nz), ws, &total);
+  uint32_t m = c.nz, k = first;
+  const int pbase = (int)threadIdx.x * kChunkBytes;
+  while (m) {
+    ipos[k++] = (unsigned short)(pbase + __ffs(m) - 1);
+    m &= m - 1;
+  }
+  __syncthreads();
+  P->count = (int)total;
+  P->len = min(kTokPiece, seg_size - base);
+  P->zeros_in = zeros_in;
+  return total ? (uint32_t)(P->len - 1 - (int)ipos[total - 1]) : zeros_in + (uint32_t)P->len;
+}
+
+__device__ __forceinline__ uint32_t item_byte(const uint32_t *rows, int pos) {
+  return reinterpret_cast<const uint8_t *>(rows)[(pos >> 5) * (kRowWords * 4) + (pos & 31)];
+}
+__device__ __forceinline__ uint32_t item_gap(const unsigned short *ipos, int k, uint32_t zeros_in) {
+  return k ? (uint32_t)(ipos[k] - ipos[k - 1] - 1) : (uint32_t)ipos[0] + zeros_in;
+}
+
+// run length -> (symbol, extra bits value) of the LAST token of the run (after full 16662 tokens)
+__device__ __forceinline__ int run_symbol(uint32_t z, uint32_t *extra) {
+  if (z == 1) { *extra = 0; return 0; }
+  if (z == 2) { *extra = 0; return 256; }
+  if (z <= 6) { *extra = z - 3; return 257; }
+  if (z <= 22) { *extra = z - 7; return 258; }
+  if (z <= 278) { *extra = z - 23; return 259; }
+  *extra = z - 279;
+  return 260;
+}
+
+// grid (nseg, n), block kTokThreads.  seghist: [n][nseg][261].
+__global__ void __launch_bounds__(kTokThreads)
+    k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist) {
+  __shared__ uint32_t sh[kSyms];
+  __shared__ uint32_t ws[kTokWarps + 1];
+  __shared__ uint32_t rows[kTokThreads * kRowWords];
+  __shared__ unsigned short ipos[kTokPiece];
+  for (int i = threadIdx.x; i < kSyms; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const uint8_t *seg = in + (size_t)blockIdx.y * hg.in_stride + (size_t)blockIdx.x * hg.seg_size;
+  uint32_t carry = 0;
+  for (int base = 0; base < hg.seg_size; base += kTokPiece) {
+    PieceItems P;
+    carry = build_items(seg, hg.seg_size, base, rows, ipos, ws, carry, &P);
+    for (int k = threadIdx.x; k < P.count; k += kTokThreads) {
+      uint32_t z = item_gap(ipos, k, P.zeros_in), ex;
+      while (z >= (uint32_t)kMaxRun) {
+        atomicAdd(&sh[260], 1u);
+        z -= kMaxRun;
+      }
+      if (z) atomicAdd(&sh[run_symbol(z, &ex)], 1u);
+      atomicAdd(&sh[item_byte(rows, ipos[k])], 1u);
+    }
+    __syncthreads();  // rows / ipos are rewritten by the next piece
+  }
+  if (threadIdx.x == 0 && carry) {  // the run still open at the segment end
+    uint32_t z = carry, ex;
+    while (z >= (uint32_t)kMaxRun) {
+      atomicAdd(&sh[260], 1u);
+      z -= kMaxRun;
+    }
+    if (z) atomicAdd(&sh[run_symbol(z, &ex)], 1u);
+  }
+  __syncthreads();
+  uint32_t *dst = seghist + ((size_t)blockIdx.y * hg.nseg + blockIdx.x) * kSyms;
+  for (int i = threadIdx.x; i < kSyms; i += blockDim.x) dst[i] = sh[i];
+}
+
 // ---- K-tree ----------------------------------------------------------------------------------
 constexpr int kTreeThreads = 288;
 
@@ -591,6 +686,170 @@ __global__ void __launch_bounds__(kHuffThreads)
       // only the words this window touched need clearing
       const int used = last_win ? (int)((vend - w0 + 31) >> 5) + 3 : kWinWords + 2;
       for (int i = t; i < min(used, kWinWords + 2); i += blockDim.x) win[i] = i == 0 ? c0 : (i == 1 ? c1 : 0u);
+      __syncthreads();
+      if (last_win) break;
+    }
+    gbits += piece_bits;
+  }
+  // final partial byte (its padding bits are zero here; k_huff_stale adds the stale ones)
+  if (t == 0) {
+    if (gbits & 7) dst[gbits >> 3] = (uint8_t)win[0];
+    if (gbits != seg_bits[(size_t)item * hg.nseg + b]) atomicMax(err, 99);  // internal consistency
+  }
+}
+
+// ---- K-pack v2 (balanced) --------------------------------------------------------------------
+constexpr int kWin2Words = 4096;  // 16 KiB bit window + 2 words of slack
+constexpr int kWin2Bits = kWin2Words * 32;
+
+struct PackTables {
+  const uint32_t *code;
+  const uint8_t *len;
+  const uint32_t *lenx;  // len + extra bits
+};
+
+__device__ __forceinline__ uint32_t item_bits(const PackTables &T, uint32_t gap, uint32_t byte) {
+  uint32_t bits = T.len[byte];
+  if (gap) {
+    if (gap >= (uint32_t)kMaxRun) {
+      const uint32_t nfull = gap / kMaxRun;
+      bits += nfull * T.lenx[260];
+      gap -= nfull * kMaxRun;
+    }
+    if (gap) {
+      uint32_t ex;
+      bits += T.lenx[run_symbol(gap, &ex)];
+    }
+  }
+  return bits;
+}
+
+// ORs `n` (<= 46) bits of `val` into the window at bit position `pos` if the token STARTS inside
+// the window [w0, w0 + kWin2Bits); it may spill into the two slack words.
+__device__ __forceinline__ void put_token(uint32_t *win, uint32_t pos, uint32_t w0, uint64_t val, int n) {
+  if (n == 0 || pos < w0 || pos >= w0 + (uint32_t)kWin2Bits) return;
+  const uint32_t rel = pos - w0, word = rel >> 5, sh = rel & 31;
+  const uint64_t v0 = val << sh;
+  const uint32_t lo = (uint32_t)v0, mid = (uint32_t)(v0 >> 32), hi = sh ? (uint32_t)(val >> (64 - sh)) : 0u;
+  if (lo) atomicOr(&win[word], lo);
+  if (mid) atomicOr(&win[word + 1], mid);
+  if (hi) atomicOr(&win[word + 2], hi);
+}
+
+// Emits the zero-run tokens of `gap` zeros starting at bit position `pos`; returns the new position.
+__device__ __forceinline__ uint32_t emit_run_tokens(uint32_t *win, uint32_t pos, uint32_t w0, const PackTables &T, uint32_t gap) {
+  while (gap >= (uint32_t)kMaxRun) {
+    put_token(win, pos, w0, (uint64_t)T.code[260] | ((uint64_t)(kMaxRun - 279) << T.len[260]), (int)T.lenx[260]);
+    pos += T.lenx[260];
+    gap -= kMaxRun;
+  }
+  if (gap) {
+    uint32_t ex;
+    const int sym = run_symbol(gap, &ex);
+    put_token(win, pos, w0, (uint64_t)T.code[sym] | ((uint64_t)ex << T.len[sym]), (int)T.lenx[sym]);
+    pos += T.lenx[sym];
+  }
+  return pos;
+}
+
+// grid (nseg, n), block kTokThreads.
+__global__ void __launch_bounds__(kTokThreads)
+    k_huff_pack2(const uint8_t *__restrict__ in, HuffGeom hg, const TreeOut *__restrict__ trees,
+                 const uint32_t *__restrict__ seg_bits, const uint32_t *__restrict__ seg_pos,
+                 const uint32_t *__restrict__ sizes, uint8_t *__restrict__ out, unsigned long long out_stride,
+                 int *err) {
+  __shared__ uint32_t win[kWin2Words + 4];
+  __shared__ uint32_t s_code[kSyms];
+  __shared__ uint8_t s_len[kSyms + 3];
+  __shared__ uint32_t s_lenx[kSyms];
+  __shared__ uint32_t ws[kTokWarps + 1];
+  __shared__ uint32_t s_wbits[kTokWarps];
+  __shared__ uint32_t rows[kTokThreads * kRowWords];
+  __shared__ unsigned short ipos[kTokPiece];
+  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (sizes[item] == 0) return;  // did not fit (k_huff_layout)
+  const TreeOut *tr = trees + item;
+  for (int s = t; s < kSyms; s += blockDim.x) {
+    s_code[s] = tr->code[s];
+    s_len[s] = tr->len[s];
+    s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+  }
+  for (int i = t; i < kWin2Words + 4; i += blockDim.x) win[i] = 0;
+  __syncthreads();
+  const PackTables T{s_code, s_len, s_lenx};
+  const uint8_t *seg = in + (size_t)item * hg.in_stride + (size_t)b * hg.seg_size;
+  uint8_t *dst = out + (size_t)item * out_stride + seg_pos[(size_t)item * hg.nseg + b];
+
+  uint32_t carry = 0;  // zeros of the run that is still open
+  uint32_t gbits = 0;  // bits emitted so far; complete bytes below gbits>>3 are already in `dst`
+  for (int base = 0; base < hg.seg_size; base += kTokPiece) {
+    PieceItems P;
+    const uint32_t carry_out = build_items(seg, hg.seg_size, base, rows, ipos, ws, carry, &P);
+    carry = carry_out;
+    const bool last_piece = base + kTokPiece >= hg.seg_size;
+    // ---- pass 1: bit total of every warp's item range (ranges are multiples of 32 items)
+    const int per = ((P.count + kTokThreads - 1) / kTokThreads) * 32;
+    const int k0 = warp * per, k1 = min(k0 + per, P.count);
+    uint32_t bits = 0;
+    for (int k = k0 + lane; k < k1; k += 32) bits += item_bits(T, item_gap(ipos, k, P.zeros_in), item_byte(rows, ipos[k]));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+    if (lane == 0) s_wbits[warp] = bits;
+    __syncthreads();
+    uint32_t wbase = 0, piece_bits = 0;
+#pragma unroll
+    for (int w = 0; w < kTokWarps; ++w) {
+      if (w < warp) wbase += s_wbits[w];
+      piece_bits += s_wbits[w];
+    }
+    // the run still open at the segment end is one more (item-less) token group
+    const uint32_t tail_gap = (last_piece ? carry_out : 0u);
+    const uint32_t items_bits = piece_bits;
+    if (tail_gap) piece_bits += item_bits(T, tail_gap, 0) - T.len[0];
+    // ---- pass 2: emit through the bit window; window bit 0 = byte boundary at or below gbits
+    const uint32_t lead = gbits & 7, vend = lead + piece_bits, gbyte = gbits >> 3;
+    for (uint32_t w0 = 0; w0 < vend || w0 == 0; w0 += kWin2Bits) {
+      uint32_t running = lead + wbase;
+      for (int kk = k0; kk < k1; kk += 32) {
+        const int k = kk + lane;
+        uint32_t gap = 0, byte = 0, nb = 0;
+        if (k < k1) {
+          gap = item_gap(ipos, k, P.zeros_in);
+          byte = item_byte(rows, ipos[k]);
+          nb = item_bits(T, gap, byte);
+        }
+        uint32_t inc = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
+        }
+        if (k < k1) {
+          uint32_t pos = running + inc - nb;
+          pos = emit_run_tokens(win, pos, w0, T, gap);
+          put_token(win, pos, w0, T.code[byte], T.len[byte]);
+        }
+        running += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (t == 0 && tail_gap) emit_run_tokens(win, lead + items_bits, w0, T, tail_gap);
+      __syncthreads();
+      const bool last_win = w0 + (uint32_t)kWin2Bits >= vend;
+      const uint32_t nbytes = last_win ? ((vend - w0) >> 3) : (uint32_t)(kWin2Bits / 8);
+      const uint8_t *wb = reinterpret_cast<const uint8_t *>(win);
+      uint8_t *o = dst + gbyte + (w0 >> 3);
+      for (uint32_t i = t; i < nbytes; i += blockDim.x) o[i] = wb[i];
+      __syncthreads();
+      // carry the unfinished tail (partial byte, or the slack words) to the front of the window
+      uint32_t c0 = 0, c1 = 0;
+      if (last_win) {
+        c0 = ((vend - w0) & 7) ? wb[nbytes] : 0;
+      } else {
+        c0 = win[kWin2Words];
+        c1 = win[kWin2Words + 1];
+      }
+      __syncthreads();
+      const int used = last_win ? (int)((vend - w0 + 31) >> 5) + 3 : kWin2Words + 4;
+      for (int i = t; i < min(used, kWin2Words + 4); i += blockDim.x) win[i] = i == 0 ? c0 : (i == 1 ? c1 : 0u);
       __syncthreads();
       if (last_win) break;
     }
