@@ -309,6 +309,13 @@ def main():
         alg_bytes = 2 * NCH * W * H * B  # per launch: nch read + nch written per pixel
         fwd_gbs = alg_bytes / (fwd_ms / fwd_n / 1e3) / 1e9 if fwd_n else 0.0
         inv_gbs = alg_bytes / (inv_ms / inv_n / 1e3) / 1e9 if inv_n else 0.0
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this exact configuration
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_final_traffic.json")))
+            if tr["config"] == {"images": B, "width": W, "height": H, "channels": NCH, "quality": QUALITY}:
+                traffic = tr["k_forward"]["traffic"]
+        except (OSError, ValueError, KeyError):
+            pass
         step_kernel_ms = sum(v[0] for v in prof.values()) / args.steps
         shares = {k: round(v[0] / args.steps / step_kernel_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         res = {
@@ -334,7 +341,7 @@ def main():
                     "api": "himgcu_encode_batch_host + himgcu_decode_batch_host (pinned host buffers)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "k_forward", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": fwd_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": fwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": fwd_ms / fwd_n if fwd_n else None,
                          "k_inverse": {"achieved": inv_gbs, "frac": inv_gbs / peak,
                                        "avg_launch_ms": inv_ms / inv_n if inv_n else None}},

@@ -275,7 +275,9 @@ __global__ void __launch_bounds__(kFwd2Threads, 2)
       for (int q = 0; q < 8; ++q)
         wht8p<2048>(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
     }
+#ifdef HIMG_FWD2_MID_BARRIER
     __syncthreads();
+#endif
     // ---- quantise both lanes, map, store the code pair
     if (active) {
       const int cls = (YCBCR && NCH >= 3 && (c == 1 || c == 2)) ? 1 : 0;
