@@ -212,8 +212,8 @@ def _golden(golden_hashes, w, h, n, q, seed=1):
     raise KeyError((w, h, n, q))
 
 
-@pytest.mark.parametrize("cfg", [(512, 512, 3, 50), (3840, 2160, 3, 50), (8192, 8192, 1, 50), (1920, 1080, 3, 0),
-                                 (1920, 1080, 3, 50), (1920, 1080, 3, 100), (8192, 16, 1, 100)])
+@pytest.mark.parametrize("cfg", [(512, 512, 3, 50), (3840, 2160, 3, 50), (8192, 8192, 1, 50), (8192, 16, 1, 100)] +
+                         [(1920, 1080, 3, q) for q in range(0, 101, 10)])  # c1, c2, c3, 4-byte headers, c4/c5 sweep
 def test_golden_configs_encode_decode(ctx, port, golden_hashes, cfg):
     """BASELINE.json configurations at full size against the reference's recorded hashes."""
     w, h, n, q = cfg
