@@ -13,7 +13,7 @@ def main():
     P = oracle.port()
     ctx = himg_b200.Context(0)
     ok = True
-    for (w, h, n, q) in [(64, 48, 3, 50), (37, 21, 1, 60), (200, 136, 4, 90), (264, 40, 3, 20)]:
+    for (w, h, n, q) in [(64, 48, 3, 50), (37, 21, 1, 60), (200, 136, 4, 90), (264, 40, 3, 20), (512, 64, 3, 50), (8192, 16, 1, 100), (256, 128, 4, 80)]:
         img = P.synth(w, h, n, 3, 6)
         got = ctx.encode(img, q, True)
         want = P.encode(img, q, True)
