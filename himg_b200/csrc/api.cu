@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/himg_cuda.h"
@@ -41,7 +43,13 @@ struct himgcu_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t in_stream = nullptr, out_stream = nullptr;  // copy streams of the host-buffer batch calls
-  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  // The host-buffer batch calls keep up to kMaxLanes sub-batches in flight.  Lane 0 is this context;
+  // lanes 1.. are child contexts (own stream, own workspace) so that the latency-bound kernels of one
+  // sub-batch (tree construction, the low-res chunk) overlap the wide kernels of its neighbours.
+  static constexpr int kMaxLanes = 4;
+  std::vector<himgcu_ctx *> lanes;
+  int host_lanes = 3;
+  cudaEvent_t ev_in[kMaxLanes] = {}, ev_cmp[kMaxLanes] = {}, ev_out[kMaxLanes] = {};
   std::string err;
   std::map<std::string, DevBuf> bufs;
   DevBuf full_lut;  // 7616-byte |x| -> code LUT, uploaded once
@@ -55,7 +63,7 @@ struct himgcu_ctx {
   std::vector<std::string> prof_names;
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
-  size_t host_sub_bytes = (size_t)192 << 20;  // staged bytes per sub-batch of the host-buffer calls
+  size_t host_sub_bytes = (size_t)64 << 20;  // staged bytes per sub-batch of the host-buffer calls
   bool force_generic = false;  // tests: route everything through the generic kernels
   // small table uploads are cached by key so that steady-state calls issue no host sync
   std::string qrec_key, lowres_key, prefix_key;  // device memory used per sub-batch of the host-buffer calls
@@ -221,35 +229,48 @@ int upload_signed_lut(himgcu_ctx *ctx) {
   return HIMGCU_OK;
 }
 
-// dp4a weights of channel c: coef[k] multiplies byte k of the pixel.
+// dp4a weights of channel c (see ColourW): coef[k] multiplies byte k of the pixel.
+//   Y  = (r + 2g + b + 2) >> 2          = byte 1 of 64 * (r + 2g + b + 2)
+//   Cb = (b - g + 256) >> 1              = byte 1 of 128 * (b + (255 - g) + 1)     (g complemented by XOR)
+//   Cr = (r - g + 256) >> 1              = byte 1 of 128 * (r + (255 - g) + 1)
+//   plain channel                        = byte 0 of 1 * value
 void make_colour(int nch, bool ycbcr, Fwd2Params *P) {
   for (int c = 0; c < 4; ++c) {
-    int coef[4] = {0, 0, 0, 0}, add = 0, shr = 0;
+    uint32_t coef[4] = {0, 0, 0, 0}, add = 0, sel = 0x7430;
+    bool xg = false;
     if (ycbcr && nch >= 3 && c < 3) {
-      if (c == 0) { coef[0] = 1; coef[1] = 2; coef[2] = 1; add = 2; shr = 2; }
-      if (c == 1) { coef[1] = -1; coef[2] = 1; add = 256; shr = 1; }
-      if (c == 2) { coef[0] = 1; coef[1] = -1; add = 256; shr = 1; }
+      sel = 0x7531;
+      add = 128;
+      if (c == 0) { coef[0] = 64; coef[1] = 128; coef[2] = 64; }
+      if (c == 1) { coef[1] = 128; coef[2] = 128; xg = true; }
+      if (c == 2) { coef[0] = 128; coef[1] = 128; xg = true; }
     } else {
       coef[c] = 1;
     }
     ColourW &w = P->cw[c];
     w.add = add;
-    w.shr = shr;
+    w.sel = sel;
+    w.has_xm = xg ? 1 : 0;
+    for (int k = 0; k < 3; ++k) {  // word k of a row: bytes 4k .. 4k+3, channel = byte index % nch
+      uint32_t m = 0;
+      for (int by = 0; by < 4; ++by)
+        if (xg && (4 * k + by) % nch == 1) m |= 0xffu << (8 * by);
+      w.xm[k] = m;
+    }
     for (int sh = 0; sh < 4; ++sh) {
       uint32_t w0 = 0, w1 = 0;
       for (int k = 0; k < nch && k < 4; ++k) {
         const int pos = sh + k;
-        const uint32_t byte = (uint32_t)(coef[k] & 0xff);
-        if (pos < 4) w0 |= byte << (8 * pos);
-        else w1 |= byte << (8 * (pos - 4));
+        if (pos < 4) w0 |= coef[k] << (8 * pos);
+        else w1 |= coef[k] << (8 * (pos - 4));
       }
-      w.w0[sh] = (int)w0;
-      w.w1[sh] = (int)w1;
+      w.w0[sh] = w0;
+      w.w1[sh] = w1;
     }
   }
 }
 
-bool make_quant_packed(const EncodeTables &t, QuantPacked *q, int *lut_half) {
+bool make_quant_recs(const EncodeTables &t, Fwd2Params *P) {
   // value range after the shift: |T| <= 16320, so |m| <= (16320 + round) >> shift
   int half = 1;
   for (int cls = 0; cls < 2; ++cls)
@@ -259,19 +280,17 @@ bool make_quant_packed(const EncodeTables &t, QuantPacked *q, int *lut_half) {
       half = std::max(half, ((16320 + (s ? 1 << (s - 1) : 0)) >> s) + 1);
     }
   half = std::min((half + 63) & ~63, kLutCenter - 64);
-  *lut_half = half;
-  memset(q, 0, sizeof(*q));
+  P->lut_half = half;
   for (int cls = 0; cls < 2; ++cls)
     for (int i = 0; i < 64; ++i) {
       const int j = scan_coef(i);  // records are stored in scan order
       const int s = cls ? t.shift_chroma[j] : t.shift_luma[j];
       const uint32_t rep = 0x00010001u;
-      QuantRec &r = q->rec[cls][i];
-      r.shift = (uint32_t)s;
+      QuantRec &r = P->rec[cls][i];
       r.c2 = (s ? (1u << (s - 1)) - 1u : 0u) * rep;
       r.tmask = s ? rep : 0u;
-      r.smask = (0xffffu >> s) * rep;
-      r.off2 = (uint32_t)(half - (16384 >> s)) * rep;
+      r.off = (uint32_t)(half - (16384 >> s));
+      r.s16 = (uint32_t)s + 16u;
     }
   return true;
 }
@@ -361,17 +380,17 @@ int launch_fwd(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int
 
 template <int NCH>
 int launch_fwd2(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
-                const Fwd2Params &P, const QuantPacked *d_q, uint8_t *d_planes) {
+                const Fwd2Params &P, uint8_t *d_planes) {
   dim3 grid((g.cols + P.tile_cols - 1) / P.tile_cols, (g.rows + P.tile_rows - 1) / P.tile_rows, n);
-  const int smem = P.tile_rows * 8 * P.tile_cols * 8 * NCH + (int)sizeof(QuantPacked) + ((2 * P.lut_half + 1 + 15) & ~15) +
-                   ((NCH * (P.tile_rows + 1) * (P.tile_cols + 2) + 15) & ~15);
+  const int smem = ((2 * P.lut_half + 1 + 15) & ~15) + ((NCH * (P.tile_rows + 1) * (P.tile_cols + 2) + 127) & ~127) +
+                   P.tile_rows * 8 * P.tile_cols * 8 * NCH;
   const uint8_t *lut = (const uint8_t *)ctx->signed_lut.p;
   if (ycbcr) {
     CK(cudaFuncSetAttribute(k_forward2<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LAUNCH("k_forward", (k_forward2<NCH, true>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, d_q, lut, d_planes);
+    LAUNCH("k_forward", (k_forward2<NCH, true>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
   } else {
     CK(cudaFuncSetAttribute(k_forward2<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LAUNCH("k_forward", (k_forward2<NCH, false>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, d_q, lut, d_planes);
+    LAUNCH("k_forward", (k_forward2<NCH, false>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
   }
   return HIMGCU_OK;
 }
@@ -382,8 +401,7 @@ int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, 
   if (!ctx->force_generic && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
       (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
     Fwd2Params P;
-    QuantPacked hq;
-    if (make_quant_packed(t, &hq, &P.lut_half)) {
+    if (make_quant_recs(t, &P)) {
       int rc = upload_signed_lut(ctx);
       if (rc) return rc;
       make_colour(g.nch, t.ycbcr, &P);
@@ -394,18 +412,10 @@ int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, 
         const int nt = (g.cols + kFwd2Blocks - 1) / kFwd2Blocks;
         P.tile_cols = (((g.cols + nt - 1) / nt) + 1) & ~1;
       }
-      QuantPacked *d_q;
-      ENSURE("fwd2_qrecs", sizeof(QuantPacked), d_q);
-      const std::string key = std::to_string(t.quality) + (t.ycbcr ? "y" : "n");
-      if (ctx->qrec_key != key) {
-        CK(cudaMemcpyAsync(d_q, &hq, sizeof(hq), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));  // `hq` is a local
-        ctx->qrec_key = key;
-      }
       switch (g.nch) {
-        case 1: return launch_fwd2<1>(ctx, d_pixels, d_L, n, g, false, P, d_q, d_planes);
-        case 3: return launch_fwd2<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_q, d_planes);
-        default: return launch_fwd2<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_q, d_planes);
+        case 1: return launch_fwd2<1>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
+        case 3: return launch_fwd2<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+        default: return launch_fwd2<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
       }
     }
   }
@@ -634,10 +644,15 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   // batch alone fills the GPU, wider teams when there are few streams (single images).
   const int lres_team = decode_team(n, g.lres_size, kParLresThreads);
   const int fres_team = decode_team((long long)n * g.rows, g.seg, kParFresThreads);
-  LAUNCH("k_dec_stream_lres", k_dec_stream_par, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
+  LAUNCH("k_dec_stream_lres", k_dec_stream_par<false>, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
          g.lres_size, d_lres, g.lres_stride, d_status);
-  LAUNCH("k_dec_stream_fres", k_dec_stream_par, dim3(g.rows, n), fres_team, 0, d_himg, d_fcd, d_ftree, d_fseg,
-         g.rows, g.seg, d_planes, g.planes_bytes, d_status);
+  if (fres_team == 32) {
+    LAUNCH("k_dec_stream_fres", k_dec_stream_par<true>, dim3((g.rows + kParWarpTeams - 1) / kParWarpTeams, n),
+           32 * kParWarpTeams, 0, d_himg, d_fcd, d_ftree, d_fseg, g.rows, g.seg, d_planes, g.planes_bytes, d_status);
+  } else {
+    LAUNCH("k_dec_stream_fres", k_dec_stream_par<false>, dim3(g.rows, n), fres_team, 0, d_himg, d_fcd, d_ftree, d_fseg,
+           g.rows, g.seg, d_planes, g.planes_bytes, d_status);
+  }
   const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
   const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
   LAUNCH("k_lres_dpcm_dec", (k_lres_dpcm<false>), blocks, kLresWarps * 32, 0, (const uint8_t *)nullptr, d_lres, d_R,
@@ -645,11 +660,33 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   return stage_inverse(ctx, d_planes, d_R, n, g, d_tabs, sizeof(DecTables), d_pixels);
 }
 
+}  // namespace
+extern "C" int himgcu_create(int device, himgcu_ctx **out);
+extern "C" void himgcu_destroy(himgcu_ctx *ctx);
+namespace {
+
+// One copy queue per direction and device, shared by every context of the process: transfers of
+// concurrent contexts (say one encoding, one decoding) then run in issue order.  Separate streams
+// were observed to starve each other for whole calls on the copy engines.
+struct CopyQueues {
+  cudaStream_t in = nullptr, out = nullptr;
+};
+std::mutex g_copyq_mutex;
+std::map<int, CopyQueues> g_copyq;
+
 int ensure_pipeline(himgcu_ctx *ctx) {
   if (ctx->in_stream) return HIMGCU_OK;
-  CK(cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx->out_stream, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; ++b) {
+  {
+    std::lock_guard<std::mutex> lock(g_copyq_mutex);
+    CopyQueues &q = g_copyq[ctx->device];
+    if (!q.in) {
+      CK(cudaStreamCreateWithFlags(&q.in, cudaStreamNonBlocking));
+      CK(cudaStreamCreateWithFlags(&q.out, cudaStreamNonBlocking));
+    }
+    ctx->in_stream = q.in;
+    ctx->out_stream = q.out;
+  }
+  for (int b = 0; b < himgcu_ctx::kMaxLanes; ++b) {
     CK(cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_cmp[b], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming));
@@ -668,6 +705,144 @@ int ensure_pinned(himgcu_ctx *ctx, size_t bytes) {
   CK(cudaMallocHost(&ctx->pinned, bytes));
   ctx->pinned_cap = bytes;
   return HIMGCU_OK;
+}
+
+// HIMG_DEBUG_PIPE=1: device-side timeline of the host-buffer calls (ms since the first traced call of
+// the process; one line per sub-batch) on stderr.  Debug aid only.
+struct PipeTrace {
+  bool on = getenv("HIMG_DEBUG_PIPE") != nullptr;
+  const char *tag;
+  std::vector<cudaEvent_t> ev;  // 4 per sub-batch: copy-in start / end, coding end, copy-out end
+  std::vector<double> host;     // host clock when the coding of the sub-batch was launched
+  static double now() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  }
+  static double &host_epoch() {
+    static double t = 0;
+    return t;
+  }
+  static cudaEvent_t epoch() {
+    static cudaEvent_t e = [] {
+      cudaEvent_t x;
+      cudaEventCreate(&x);
+      cudaEventRecord(x, 0);
+      cudaEventSynchronize(x);
+      host_epoch() = now();
+      return x;
+    }();
+    return e;
+  }
+  void launched(int k) {
+    if (!on) return;
+    if ((int)host.size() <= k) host.resize(k + 1, 0);
+    host[k] = now() - host_epoch();
+  }
+  explicit PipeTrace(const char *t) : tag(t) {
+    if (on) epoch();
+  }
+  void mark(int k, int what, cudaStream_t s) {
+    if (!on) return;
+    if ((int)ev.size() < 4 * (k + 1)) ev.resize(4 * (k + 1), nullptr);
+    cudaEventCreate(&ev[4 * k + what]);
+    cudaEventRecord(ev[4 * k + what], s);
+  }
+  ~PipeTrace() {
+    if (!on) return;
+    for (size_t k = 0; k * 4 < ev.size(); ++k) {
+      float t[4] = {-1, -1, -1, -1};
+      for (int j = 0; j < 4; ++j)
+        if (ev[4 * k + j]) {
+          cudaEventSynchronize(ev[4 * k + j]);
+          cudaEventElapsedTime(&t[j], epoch(), ev[4 * k + j]);
+          cudaEventDestroy(ev[4 * k + j]);
+        }
+      fprintf(stderr, "[pipe %s] sub %2zu  in %8.2f..%8.2f  coded %8.2f  out %8.2f  (launched by the host at %8.2f)\n", tag, k,
+              t[0], t[1], t[2], t[3], k < host.size() ? host[k] : -1.0);
+    }
+  }
+};
+
+// Lanes in use for a host-buffer call of K sub-batches; creates the child contexts on demand.
+int prepare_lanes(himgcu_ctx *ctx, int K, int *count) {
+  int S = std::max(1, std::min({ctx->host_lanes, (int)himgcu_ctx::kMaxLanes, K}));
+  if (ctx->profile) S = 1;  // per-kernel events are only meaningful without overlap
+  while ((int)ctx->lanes.size() < S - 1) {
+    himgcu_ctx *l = nullptr;
+    if (himgcu_create(ctx->device, &l) != HIMGCU_OK) return fail(ctx, HIMGCU_ERR_CUDA, "cannot create a coding lane");
+    ctx->lanes.push_back(l);
+  }
+  for (himgcu_ctx *l : ctx->lanes) {
+    l->force_generic = ctx->force_generic;
+    l->max_workspace = ctx->max_workspace;
+  }
+  *count = S;
+  return HIMGCU_OK;
+}
+himgcu_ctx *lane_of(himgcu_ctx *ctx, int b) { return b == 0 ? ctx : ctx->lanes[b - 1]; }
+int finish_lanes(himgcu_ctx *ctx, int S) {
+  for (int b = 0; b < S; ++b) CK(cudaStreamSynchronize(lane_of(ctx, b)->stream));
+  for (himgcu_ctx *l : ctx->lanes) {
+    ctx->launches += l->launches;
+    l->launches = 0;
+  }
+  return HIMGCU_OK;
+}
+
+// Host-buffer batches are pipelined: sub-batches flow through the H2D queue, a coding lane and the
+// D2H queue, S of them in flight (S device staging slots, S lanes).  The calling thread drives the
+// pipeline and orders the stages ON THE HOST (event queries): no stream ever waits on an event of
+// another stream.  Device-side waits looked cheaper but a stream parked on one was observed to
+// starve for the whole call while another context kept the GPU busy -- which is exactly the case
+// of one thread encoding and another decoding (both PCIe directions in use).
+// With pageable host memory the copies degrade to synchronous ones but stay correct.
+template <class FIn, class FRun, class FOut>
+int run_pipeline(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy_out) {
+  int n_in = 0, n_run = 0, n_out = 0;  // sub-batches copied in / launched / drained so far
+  auto done = [&](cudaEvent_t e, bool *ok) -> int {
+    const cudaError_t q = cudaEventQuery(e);
+    if (q != cudaSuccess && q != cudaErrorNotReady) CK(q);
+    *ok = q == cudaSuccess;
+    return HIMGCU_OK;
+  };
+  while (n_out < K) {
+    bool progressed = false, ok = false;
+    int rc;
+    if (n_out < n_run) {  // coded -> copy out
+      const int b = n_out % S;
+      if ((rc = done(ctx->ev_cmp[b], &ok))) return rc;
+      if (ok) {
+        if ((rc = copy_out(n_out, b))) return rc;
+        CK(cudaEventRecord(ctx->ev_out[b], ctx->out_stream));
+        ++n_out;
+        progressed = true;
+      }
+    }
+    if (n_run < n_in) {  // copied in (and the slot's previous output drained) -> launch
+      const int b = n_run % S;
+      if ((rc = done(ctx->ev_in[b], &ok))) return rc;
+      if (ok && n_run >= S && (rc = done(ctx->ev_out[b], &ok))) return rc;
+      if (ok) {
+        himgcu_ctx *L = lane_of(ctx, b);
+        if ((rc = run(n_run, b, L))) {
+          if (L != ctx) ctx->err = L->err;
+          return rc;
+        }
+        CK(cudaEventRecord(ctx->ev_cmp[b], L->stream));
+        ++n_run;
+        progressed = true;
+      }
+    }
+    if (n_in < K && n_in < n_out + S && n_in < n_run + 2) {  // slot free -> copy in (at most 2 ahead)
+      const int b = n_in % S;
+      if ((rc = copy_in(n_in, b))) return rc;
+      CK(cudaEventRecord(ctx->ev_in[b], ctx->in_stream));
+      ++n_in;
+      progressed = true;
+    }
+    if (!progressed) std::this_thread::sleep_for(std::chrono::microseconds(20));
+  }
+  if (K > 0) CK(cudaEventSynchronize(ctx->ev_out[(K - 1) % S]));  // own copies only: the queue is shared
+  return finish_lanes(ctx, S);
 }
 
 }  // namespace
@@ -711,13 +886,13 @@ void himgcu_destroy(himgcu_ctx *ctx) {
   if (ctx->signed_lut.p) cudaFree(ctx->signed_lut.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
-  for (int b = 0; b < 2; ++b) {
+  for (himgcu_ctx *l : ctx->lanes) himgcu_destroy(l);
+  for (int b = 0; b < himgcu_ctx::kMaxLanes; ++b) {
     if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
     if (ctx->ev_cmp[b]) cudaEventDestroy(ctx->ev_cmp[b]);
     if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
   }
-  if (ctx->in_stream) cudaStreamDestroy(ctx->in_stream);
-  if (ctx->out_stream) cudaStreamDestroy(ctx->out_stream);
+  // in_stream / out_stream are the process-wide copy queues: not destroyed here
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -908,9 +1083,6 @@ void himgcu_host_free(void *p) {
   if (p) cudaFreeHost(p);
 }
 
-// Host-buffer batches are pipelined: sub-batches flow through three streams (H2D, coding, D2H) with
-// double-buffered device staging, so the PCIe transfers of neighbouring sub-batches overlap the
-// kernels.  With pageable host memory the copies degrade to synchronous ones but stay correct.
 int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int w, int h, int nch, int quality,
                              int use_ycbcr, uint8_t *out, size_t out_cap, uint64_t *offsets, uint32_t *sizes) {
   if (!ctx || !pixels || !out || !offsets || !sizes || n < 0) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
@@ -924,61 +1096,57 @@ int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int 
   int sub = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(n, 1), ctx->host_sub_bytes / (g.img_bytes + stride)));
   sub = std::min(sub, 65535);
   const int K = (n + sub - 1) / sub;
-  uint8_t *d_in[2], *d_out[2];
-  uint32_t *d_sizes[2];
-  ENSURE("hb_in0", (size_t)sub * g.img_bytes, d_in[0]);
-  ENSURE("hb_in1", (size_t)sub * g.img_bytes, d_in[1]);
-  ENSURE("hb_out0", (size_t)sub * stride, d_out[0]);
-  ENSURE("hb_out1", (size_t)sub * stride, d_out[1]);
-  ENSURE("hb_sizes0", (size_t)sub * sizeof(uint32_t), d_sizes[0]);
-  ENSURE("hb_sizes1", (size_t)sub * sizeof(uint32_t), d_sizes[1]);
-  rc = ensure_pinned(ctx, 2 * (size_t)sub * sizeof(uint32_t));
+  int S = 1;
+  if ((rc = prepare_lanes(ctx, K, &S))) return rc;
+  uint8_t *d_in[himgcu_ctx::kMaxLanes], *d_out[himgcu_ctx::kMaxLanes];
+  uint32_t *d_sizes[himgcu_ctx::kMaxLanes], *h_sizes[himgcu_ctx::kMaxLanes];
+  for (int b = 0; b < S; ++b) {
+    const std::string sfx = std::to_string(b);
+    ENSURE(("hb_in" + sfx).c_str(), (size_t)sub * g.img_bytes, d_in[b]);
+    ENSURE(("hb_out" + sfx).c_str(), (size_t)sub * stride, d_out[b]);
+    ENSURE(("hb_sizes" + sfx).c_str(), (size_t)sub * sizeof(uint32_t), d_sizes[b]);
+  }
+  rc = ensure_pinned(ctx, (size_t)S * sub * sizeof(uint32_t));
   if (rc) return rc;
-  uint32_t *h_sizes[2] = {reinterpret_cast<uint32_t *>(ctx->pinned), reinterpret_cast<uint32_t *>(ctx->pinned) + sub};
-  cudaStream_t s_in = ctx->in_stream, s_cmp = ctx->stream, s_out = ctx->out_stream;
-  CK(cudaStreamSynchronize(s_cmp));
-
-  auto issue = [&](int k) -> int {
-    const int b = k & 1, i0 = k * sub, m = std::min(sub, n - i0);
-    if (k >= 2) CK(cudaStreamWaitEvent(s_in, ctx->ev_cmp[b], 0));  // staging buffer consumed by sub-batch k-2
-    CK(cudaMemcpyAsync(d_in[b], pixels + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, s_in));
-    CK(cudaEventRecord(ctx->ev_in[b], s_in));
-    CK(cudaStreamWaitEvent(s_cmp, ctx->ev_in[b], 0));
-    if (k >= 2) CK(cudaStreamWaitEvent(s_cmp, ctx->ev_out[b], 0));  // output buffer drained
-    int r = encode_device(ctx, d_in[b], m, g, quality, ycbcr, d_out[b], stride, d_sizes[b]);
-    if (r) return r;
-    CK(cudaMemcpyAsync(h_sizes[b], d_sizes[b], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s_cmp));
-    CK(cudaEventRecord(ctx->ev_cmp[b], s_cmp));
-    return HIMGCU_OK;
-  };
+  for (int b = 0; b < S; ++b) h_sizes[b] = reinterpret_cast<uint32_t *>(ctx->pinned) + (size_t)b * sub;
+  cudaStream_t s_in = ctx->in_stream, s_out = ctx->out_stream;
+  for (int b = 0; b < S; ++b) CK(cudaStreamSynchronize(lane_of(ctx, b)->stream));
+  PipeTrace trace("enc");
   uint64_t pos = 0;
   offsets[0] = 0;
-  const bool dbg = getenv("HIMG_DEBUG_PIPE") != nullptr;
-  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-  const double t0 = now();
-  for (int k = 0; k < std::min(K, 2); ++k)
-    if ((rc = issue(k))) return rc;
-  if (dbg) fprintf(stderr, "[pipe] K=%d sub=%d issued 2 at %.2f ms\n", K, sub, now() - t0);
-  for (int k = 0; k < K; ++k) {
-    const int b = k & 1, i0 = k * sub, m = std::min(sub, n - i0);
-    CK(cudaEventSynchronize(ctx->ev_cmp[b]));  // sizes of sub-batch k are on the host
-    if (dbg) fprintf(stderr, "[pipe] cmp %d done at %.2f ms\n", k, now() - t0);
-    for (int i = 0; i < m; ++i) {
-      const uint32_t sz = h_sizes[b][i];
-      sizes[i0 + i] = sz;
-      if (sz == 0) return fail(ctx, HIMGCU_ERR_CAPACITY, "image %d could not be encoded", i0 + i);
-      if (pos + sz > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small");
-      CK(cudaMemcpyAsync(out + pos, d_out[b] + (size_t)i * stride, sz, cudaMemcpyDeviceToHost, s_out));
-      pos += ((uint64_t)sz + 15) & ~15ull;
-      offsets[i0 + i + 1] = pos;
-    }
-    CK(cudaEventRecord(ctx->ev_out[b], s_out));
-    if (k + 2 < K && (rc = issue(k + 2))) return rc;
-  }
-  CK(cudaStreamSynchronize(s_out));
-  CK(cudaStreamSynchronize(s_cmp));
-  if (dbg) fprintf(stderr, "[pipe] all done at %.2f ms\n", now() - t0);
-  return HIMGCU_OK;
+  return run_pipeline(
+      ctx, K, S,
+      [&](int k, int b) -> int {
+        const int i0 = k * sub, m = std::min(sub, n - i0);
+        trace.mark(k, 0, s_in);
+        CK(cudaMemcpyAsync(d_in[b], pixels + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, s_in));
+        trace.mark(k, 1, s_in);
+        return HIMGCU_OK;
+      },
+      [&](int k, int b, himgcu_ctx *L) -> int {
+        const int m = std::min(sub, n - k * sub);
+        trace.launched(k);
+        int r = encode_device(L, d_in[b], m, g, quality, ycbcr, d_out[b], stride, d_sizes[b]);
+        if (r) return r;
+        if (cudaMemcpyAsync(h_sizes[b], d_sizes[b], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream) != cudaSuccess)
+          return fail(L, HIMGCU_ERR_CUDA, "size read-back failed");
+        trace.mark(k, 2, L->stream);
+        return HIMGCU_OK;
+      },
+      [&](int k, int b) -> int {
+        const int i0 = k * sub, m = std::min(sub, n - i0);
+        for (int i = 0; i < m; ++i) {  // the sizes of sub-batch k are on the host
+          const uint32_t sz = h_sizes[b][i];
+          sizes[i0 + i] = sz;
+          if (sz == 0) return fail(ctx, HIMGCU_ERR_CAPACITY, "image %d could not be encoded", i0 + i);
+          if (pos + sz > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small");
+          CK(cudaMemcpyAsync(out + pos, d_out[b] + (size_t)i * stride, sz, cudaMemcpyDeviceToHost, s_out));
+          pos += ((uint64_t)sz + 15) & ~15ull;
+          offsets[i0 + i + 1] = pos;
+        }
+        trace.mark(k, 3, s_out);
+        return HIMGCU_OK;
+      });
 }
 
 int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_t *offsets, const uint32_t *sizes,
@@ -1005,11 +1173,13 @@ int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_
     }
     max_range = std::max<size_t>(max_range, (size_t)(hi[k] - lo[k]));
   }
-  uint8_t *d_px[2], *d_in[2];
-  unsigned long long *d_off[2];
-  uint32_t *d_sz[2];
-  int *d_status[2];
-  for (int b = 0; b < 2; ++b) {
+  int S = 1;
+  if ((rc = prepare_lanes(ctx, K, &S))) return rc;
+  uint8_t *d_px[himgcu_ctx::kMaxLanes], *d_in[himgcu_ctx::kMaxLanes];
+  unsigned long long *d_off[himgcu_ctx::kMaxLanes];
+  uint32_t *d_sz[himgcu_ctx::kMaxLanes];
+  int *d_status[himgcu_ctx::kMaxLanes];
+  for (int b = 0; b < S; ++b) {
     const std::string sfx = std::to_string(b);
     ENSURE(("hbd_px" + sfx).c_str(), (size_t)sub * g.out_img_bytes, d_px[b]);
     ENSURE(("hbd_in" + sfx).c_str(), max_range + 64, d_in[b]);
@@ -1017,31 +1187,46 @@ int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_
     ENSURE(("hbd_sz" + sfx).c_str(), (size_t)sub * sizeof(uint32_t), d_sz[b]);
     ENSURE(("hbd_status" + sfx).c_str(), (size_t)sub * sizeof(int), d_status[b]);
   }
-  rc = ensure_pinned(ctx, (size_t)n * sizeof(unsigned long long));
+  // offsets / sizes / status travel through pinned staging: a copy from or to the caller's pageable
+  // arrays would block the issuing thread on every sub-batch and serialise the pipeline
+  rc = ensure_pinned(ctx, (size_t)n * (sizeof(unsigned long long) + sizeof(uint32_t) + sizeof(int32_t)));
   if (rc) return rc;
   unsigned long long *rel = reinterpret_cast<unsigned long long *>(ctx->pinned);  // stays valid until the end
-  cudaStream_t s_in = ctx->in_stream, s_cmp = ctx->stream, s_out = ctx->out_stream;
-  CK(cudaStreamSynchronize(s_cmp));
-  for (int k = 0; k < K; ++k) {
-    const int b = k & 1, i0 = k * sub, m = std::min(sub, n - i0);
-    for (int i = 0; i < m; ++i) rel[i0 + i] = offsets[i0 + i] - lo[k];
-    if (k >= 2) CK(cudaStreamWaitEvent(s_in, ctx->ev_cmp[b], 0));
-    CK(cudaMemcpyAsync(d_in[b], himg + lo[k], (size_t)(hi[k] - lo[k]), cudaMemcpyHostToDevice, s_in));
-    CK(cudaMemcpyAsync(d_off[b], rel + i0, (size_t)m * sizeof(unsigned long long), cudaMemcpyHostToDevice, s_in));
-    CK(cudaMemcpyAsync(d_sz[b], sizes + i0, (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice, s_in));
-    CK(cudaEventRecord(ctx->ev_in[b], s_in));
-    CK(cudaStreamWaitEvent(s_cmp, ctx->ev_in[b], 0));
-    if (k >= 2) CK(cudaStreamWaitEvent(s_cmp, ctx->ev_out[b], 0));
-    rc = decode_device(ctx, d_in[b], d_off[b], d_sz[b], m, g, flags, d_px[b], d_status[b]);
-    if (rc) return rc;
-    CK(cudaEventRecord(ctx->ev_cmp[b], s_cmp));
-    CK(cudaStreamWaitEvent(s_out, ctx->ev_cmp[b], 0));
-    CK(cudaMemcpyAsync(status + i0, d_status[b], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s_out));
-    CK(cudaMemcpyAsync(pixels_out + (size_t)i0 * g.out_img_bytes, d_px[b], (size_t)m * g.out_img_bytes, cudaMemcpyDeviceToHost, s_out));
-    CK(cudaEventRecord(ctx->ev_out[b], s_out));
-  }
-  CK(cudaStreamSynchronize(s_out));
-  CK(cudaStreamSynchronize(s_cmp));
+  uint32_t *p_sz = reinterpret_cast<uint32_t *>(rel + n);
+  int32_t *p_status = reinterpret_cast<int32_t *>(p_sz + n);
+  memcpy(p_sz, sizes, (size_t)n * sizeof(uint32_t));
+  cudaStream_t s_in = ctx->in_stream, s_out = ctx->out_stream;
+  for (int b = 0; b < S; ++b) CK(cudaStreamSynchronize(lane_of(ctx, b)->stream));
+  PipeTrace trace("dec");
+  rc = run_pipeline(
+      ctx, K, S,
+      [&](int k, int b) -> int {
+        const int i0 = k * sub, m = std::min(sub, n - i0);
+        for (int i = 0; i < m; ++i) rel[i0 + i] = offsets[i0 + i] - lo[k];
+        trace.mark(k, 0, s_in);
+        CK(cudaMemcpyAsync(d_in[b], himg + lo[k], (size_t)(hi[k] - lo[k]), cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(d_off[b], rel + i0, (size_t)m * sizeof(unsigned long long), cudaMemcpyHostToDevice, s_in));
+        CK(cudaMemcpyAsync(d_sz[b], p_sz + i0, (size_t)m * sizeof(uint32_t), cudaMemcpyHostToDevice, s_in));
+        trace.mark(k, 1, s_in);
+        return HIMGCU_OK;
+      },
+      [&](int k, int b, himgcu_ctx *L) -> int {
+        const int m = std::min(sub, n - k * sub);
+        trace.launched(k);
+        int r = decode_device(L, d_in[b], d_off[b], d_sz[b], m, g, flags, d_px[b], d_status[b]);
+        if (r) return r;
+        trace.mark(k, 2, L->stream);
+        return HIMGCU_OK;
+      },
+      [&](int k, int b) -> int {
+        const int i0 = k * sub, m = std::min(sub, n - i0);
+        CK(cudaMemcpyAsync(p_status + i0, d_status[b], (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+        CK(cudaMemcpyAsync(pixels_out + (size_t)i0 * g.out_img_bytes, d_px[b], (size_t)m * g.out_img_bytes, cudaMemcpyDeviceToHost, s_out));
+        trace.mark(k, 3, s_out);
+        return HIMGCU_OK;
+      });
+  if (rc) return rc;
+  memcpy(status, p_status, (size_t)n * sizeof(int32_t));
   return HIMGCU_OK;
 }
 
@@ -1110,8 +1295,14 @@ int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in
   LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_in, d_cd, lenient, d_tree, d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_in, d_cd, d_tree, n, nseg, seg, whole ? 0 : 1, lenient, d_seg,
          d_status);
-  LAUNCH("k_dec_stream", k_dec_stream_par, dim3(nseg, n), decode_team((long long)n * nseg, seg, nseg == 1 ? kParLresThreads : kParFresThreads),
-         0, d_in, d_cd, d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);
+  const int team = decode_team((long long)n * nseg, seg, nseg == 1 ? kParLresThreads : kParFresThreads);
+  if (team == 32) {
+    LAUNCH("k_dec_stream", k_dec_stream_par<true>, dim3((nseg + kParWarpTeams - 1) / kParWarpTeams, n), 32 * kParWarpTeams, 0,
+           d_in, d_cd, d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);
+  } else {
+    LAUNCH("k_dec_stream", k_dec_stream_par<false>, dim3(nseg, n), team, 0, d_in, d_cd, d_tree, d_seg, nseg, seg, d_out,
+           (unsigned long long)out_stride, d_status);
+  }
   return HIMGCU_OK;
 }
 
@@ -1189,7 +1380,8 @@ int himgcu_set_option(himgcu_ctx *ctx, const char *name, long long value) {
   if (!ctx || !name) return HIMGCU_ERR_ARG;
   if (!strcmp(name, "force_generic")) ctx->force_generic = value != 0;
   else if (!strcmp(name, "max_workspace_bytes")) ctx->max_workspace = (size_t)value;
-  else if (!strcmp(name, "host_sub_batch_bytes")) ctx->host_sub_bytes = (size_t)value;
+  else if (!strcmp(name, "host_sub_batch_bytes")) ctx->host_sub_bytes = (size_t)std::max<long long>(value, 1 << 20);
+  else if (!strcmp(name, "host_lanes")) ctx->host_lanes = (int)std::max<long long>(1, std::min<long long>(value, himgcu_ctx::kMaxLanes));
   else return fail(ctx, HIMGCU_ERR_ARG, "unknown option %s", name);
   return HIMGCU_OK;
 }

@@ -426,37 +426,55 @@ constexpr int kParFresThreads = 32;   // team per block-row segment
 constexpr int kParLresThreads = 256;  // team for the single unframed LRES stream
 constexpr int kParMaxTeam = 1024;
 
-// grid (nseg, n), block TEAM (multiple of 32, <= 1024): one CTA per stream.
+constexpr int kParWarpTeams = 8;  // WARP_TEAMS: streams (one warp each) per CTA
+
+// WARP_TEAMS = false: grid (nseg, n), block TEAM (multiple of 32, <= 1024): one CTA per stream.
+// WARP_TEAMS = true:  grid (ceil(nseg / 8), n), block 256: a warp per stream, eight consecutive
+//   streams of the same image per CTA.  They share the image's LUT and tree in shared memory (1 KiB
+//   of shared memory per stream instead of 12 KiB, so the kernel leaves room for CTAs of other
+//   streams' kernels) and synchronise with __syncwarp only.
+template <bool WARP_TEAMS>
 __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
                                  const DecTree *__restrict__ trees, const SegRef *__restrict__ segs, int nseg,
                                  int out_seg, uint8_t *__restrict__ out, unsigned long long out_stride,
                                  int *__restrict__ status) {
   __shared__ __align__(16) uint32_t lut[kLutSize];
   __shared__ __align__(16) short s_nodes[3 * (kMaxNodes + 3)];
-  __shared__ uint32_t s_end[kParMaxTeam];
+  __shared__ uint32_t s_end_all[WARP_TEAMS ? 32 * kParWarpTeams : kParMaxTeam];
   __shared__ uint32_t ws[33];
-  __shared__ int s_changed, s_bad, s_final;
-  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x, team = blockDim.x;
+  __shared__ int s_flags[3 * (WARP_TEAMS ? kParWarpTeams : 1)];
+  const int item = blockIdx.y;
+  const int tm = WARP_TEAMS ? (int)(threadIdx.x >> 5) : 0;  // team inside the CTA
+  const int t = WARP_TEAMS ? (int)(threadIdx.x & 31) : (int)threadIdx.x, team = WARP_TEAMS ? 32 : (int)blockDim.x;
+  const int b = WARP_TEAMS ? (int)blockIdx.x * kParWarpTeams + tm : (int)blockIdx.x;
+  auto tsync = [] {
+    if (WARP_TEAMS) __syncwarp();
+    else __syncthreads();
+  };
   const DecTree *T = trees + item;
-  const SegRef sr = segs[(size_t)item * nseg + b];
-  if (!T->ok || sr.size == 0xffffffffu || sr.size == 0) {  // an empty stream cannot produce out_seg > 0 bytes
-    if (t == 0) atomicMax(&status[item], 1);
-    return;
-  }
-  {
+  if (T->ok) {  // the whole CTA stages the image's LUT and tree
     const uint4 *ls = reinterpret_cast<const uint4 *>(T->lut);
 #pragma unroll 4
-    for (int i = t; i < kLutSize / 4; i += team) reinterpret_cast<uint4 *>(lut)[i] = __ldg(ls + i);
+    for (int i = threadIdx.x; i < kLutSize / 4; i += blockDim.x) reinterpret_cast<uint4 *>(lut)[i] = __ldg(ls + i);
     const int nn = T->nnodes;
-    for (int i = t; i < nn; i += team) {
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
       s_nodes[i] = T->ca[i];
       s_nodes[(kMaxNodes + 3) + i] = T->cb[i];
       s_nodes[2 * (kMaxNodes + 3) + i] = T->sym[i];
     }
   }
+  __syncthreads();
+  if (WARP_TEAMS && b >= nseg) return;
+  const SegRef sr = segs[(size_t)item * nseg + b];
+  if (!T->ok || sr.size == 0xffffffffu || sr.size == 0) {  // an empty stream cannot produce out_seg > 0 bytes
+    if (t == 0) atomicMax(&status[item], 1);
+    return;
+  }
+  uint32_t *s_end = s_end_all + 32 * tm;
+  int &s_changed = s_flags[3 * tm], &s_bad = s_flags[3 * tm + 1], &s_final = s_flags[3 * tm + 2];
   const SNodes SN{s_nodes, s_nodes + (kMaxNodes + 3), s_nodes + 2 * (kMaxNodes + 3)};
   if (t == 0) s_bad = 0, s_final = -1;
-  __syncthreads();
+  tsync();
   const uint8_t *src = data + cd[item].off + sr.off;
   uint8_t *o = out + (size_t)item * out_stride + (size_t)b * out_seg;
   const uint32_t total_bits = sr.size * 8u;
@@ -471,7 +489,7 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
       for (int i = t; i < out_seg; i += team) o[i] = 0;
     }
   }
-  __syncthreads();
+  tsync();
 
   if (T->single) {
     // Single-leaf tree: every token has the same code (0 bits for the reference decoder, 1 bit in
@@ -527,7 +545,7 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
     }
     s_end[t] = has_work ? endpos : kPosInvalid;
     if (t == 0) s_changed = 0;
-    __syncthreads();
+    tsync();
     dirty = false;
     if (has_work && t > 0) {
       const uint32_t prev = s_end[t - 1];
@@ -542,17 +560,29 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
         s_changed = 1;
       }
     }
-    __syncthreads();
+    tsync();
     if (!s_changed) break;
-    __syncthreads();
+    tsync();
   }
 
   // ---- output offsets
-  uint32_t total;
-  const uint32_t off = block_exscan_u32(has_work ? count : 0u, ws, &total);
+  uint32_t off;
+  if (WARP_TEAMS) {
+    const uint32_t v = has_work ? count : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+      if (t >= d) inc += u;
+    }
+    off = inc - v;
+  } else {
+    uint32_t total;
+    off = block_exscan_u32(has_work ? count : 0u, ws, &total);
+  }
   // threads whose output lies inside the segment must have decoded cleanly
   if (has_work && off < (uint32_t)out_seg && endpos == kPosInvalid) s_bad = 1;
-  __syncthreads();
+  tsync();
   if (s_bad) {
     if (t == 0) atomicMax(&status[item], 1);
     return;
@@ -577,7 +607,7 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
     }
     if (!ok) s_bad = 1;
   }
-  __syncthreads();
+  tsync();
   if (t == 0) {
     // complete output, and the read position inside the last byte (BitStream::AtTheEnd)
     const bool ok = !s_bad && s_final >= 0 && (uint32_t)s_final > 8u * (sr.size - 1) && (uint32_t)s_final <= total_bits;

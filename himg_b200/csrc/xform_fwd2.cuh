@@ -11,9 +11,13 @@
 //    32-bit register (lo = block A, hi = block B).  Lanes carry a bias (256 after the low-res
 //    subtract, doubling per butterfly stage up to 16384) so they stay non-negative: ordinary 32-bit
 //    IADD / IADD3 then act as exact 2-wide SIMD adds and subtracts with no cross-lane borrow;
-//  * colour mapping uses dp4a straight on the interleaved RGB words (no per-byte unpacking);
-//  * the sign-magnitude rounding shift is done on both lanes at once; the 8-bit mapping is one
-//    lookup in a SIGNED table (global memory, L1 resident) indexed by m + 16384;
+//  * colour mapping uses dp4a straight on the interleaved RGB words (no per-byte unpacking).  The
+//    weights are pre-scaled (x64 for Y, x128 for Cb/Cr, with the G bytes complemented by one XOR per
+//    row word so that every weight is non-negative): the wanted 8-bit value then sits in byte 1 of
+//    the sum and ONE byte-permute builds the lane pair -- no shift, no mask;
+//  * the sign-magnitude rounding add is done on both lanes at once; the per-coefficient constants
+//    come from the kernel parameter block (constant bank -> uniform registers, no shared-memory
+//    traffic); the 8-bit mapping is one lookup per lane in a SIGNED table staged in shared memory;
 //  * the two codes of a lane pair are adjacent bytes of a coefficient plane: one 16-bit store per
 //    pair, 64 contiguous bytes per warp instruction.
 //
@@ -32,19 +36,12 @@ constexpr int kFwd2Threads = 256;
 constexpr int kFwd2Blocks = 2 * kFwd2Threads;  // 8x8 blocks per CTA tile (2 per thread)
 constexpr int kLutCenter = 16384;  // signed map LUT: index = m + kLutCenter, m in [-16384, 16383]
 
-// Per-coefficient quantiser record; every mask/constant is a 16-bit pattern replicated in both
-// lanes.  The records live in global memory ([class][scan position]) and are copied to shared
-// memory by each CTA, so the kernel has ONE quantiser body for luma and chroma.
+// Per-coefficient quantiser record (in SCAN order), read from the kernel parameter block.
 struct QuantRec {
-  uint32_t c2;     // shift ? round - 1 : 0
+  uint32_t c2;     // shift ? round - 1 : 0, replicated in both 16-bit lanes
   uint32_t tmask;  // shift ? 0x00010001 : 0      (negative values round half away from 0)
-  uint32_t smask;  // 0xffff >> shift
-  uint32_t off2;   // lut_half - (16384 >> shift): re-centres the lane on the shared LUT
-  uint32_t shift;
-  uint32_t pad[3];
-};
-struct QuantPacked {
-  QuantRec rec[2][64];  // indexed by SCAN position
+  uint32_t s16;    // shift + 16
+  uint32_t off;    // lut_half - (16384 >> shift): re-centres a shifted lane on the shared LUT
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,39 +115,44 @@ __device__ __forceinline__ void wht8p(uint32_t &x0, uint32_t &x1, uint32_t &x2, 
   bfly<K3>(b2, b3, x3, x4);
 }
 
-// Colour mapping as dp4a weights: value = (sum_b byte[b] * weight[b] + add) >> shr over the (at
-// most two) words that hold the pixel.  One code path serves Y / Cb / Cr, plain channel extraction
-// and alpha, so the kernel body exists once and the channel loop is not unrolled.
+// Colour mapping as dp4a weights: sum = dot(bytes ^ xm, weights) + add over the (at most two) words
+// that hold the pixel; the 8-bit result is byte 1 (scaled weights) or byte 0 (plain extraction) of
+// the sum and bytes 2-3 are zero, so __byte_perm(sum_a, sum_b, sel) is the lane pair.  One code path
+// serves Y / Cb / Cr, plain channel extraction and alpha, so the kernel body exists once and the
+// channel loop is not unrolled.
 struct ColourW {
-  int w0[4], w1[4];  // weights for the pixel's first / second word, indexed by (byte offset & 3)
-  int add, shr;
+  uint32_t w0[4], w1[4];  // weights for the pixel's first / second word, indexed by (byte offset & 3)
+  uint32_t add, sel;
+  uint32_t xm[3];         // XOR masks of the row words (word k uses xm[k % 3]; all equal for 4 channels)
+  uint32_t has_xm;
 };
 struct Fwd2Params {
   ColourW cw[4];
+  QuantRec rec[2][64];  // [luma | chroma][scan position]
   int lut_half;    // the shared-memory LUT covers m in [-lut_half, lut_half]
   int tile_cols;   // blocks per tile row (even, <= 512)
   int tile_rows;   // block rows per tile (tile_rows * tile_cols <= 512)
 };
 
-__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
-  int d;
-  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
 
 // Colour-mapped value pair (lo = block A pixel i, hi = block B pixel i).  wa / wb: the 2*NCH raw
-// row words of the two blocks.
+// row words of the two blocks (already XORed with the channel's masks).
 template <int NCH>
-__device__ __forceinline__ uint32_t colour_pair(const uint32_t *wa, const uint32_t *wb, int i, const int (&cw0)[4],
-                                                const int (&cw1)[4], int add, int shr) {
+__device__ __forceinline__ uint32_t colour_pair(const uint32_t *wa, const uint32_t *wb, int i, const uint32_t (&cw0)[4],
+                                                const uint32_t (&cw1)[4], uint32_t add, uint32_t sel) {
   const int k = i * NCH, w0 = k >> 2, sh = k & 3;
   if (NCH == 1) return __byte_perm(wa[w0], wb[w0], 0x0400 | sh | ((sh + 4) << 8)) & 0x00ff00ffu;
-  int sa = dp4a_us(wa[w0], cw0[sh], add), sb = dp4a_us(wb[w0], cw0[sh], add);
+  uint32_t sa = dp4a_uu(wa[w0], cw0[sh], add), sb = dp4a_uu(wb[w0], cw0[sh], add);
   if (sh + NCH > 4) {
-    sa = dp4a_us(wa[w0 + 1], cw1[sh], sa);
-    sb = dp4a_us(wb[w0 + 1], cw1[sh], sb);
+    sa = dp4a_uu(wa[w0 + 1], cw1[sh], sa);
+    sb = dp4a_uu(wb[w0 + 1], cw1[sh], sb);
   }
-  return (((uint32_t)sa + ((uint32_t)sb << 16)) >> shr) & 0x00ff00ffu;
+  return __byte_perm(sa, sb, sel);
 }
 
 // Quantise + map + store the 64 lane pairs of one channel, visiting the planes in scan order so
@@ -159,13 +161,13 @@ template <int I>
 __device__ __forceinline__ void quant_one(const uint32_t (&x)[64], const QuantRec *rec, const uint8_t *slut,
                                           uint8_t *&dst, int cols) {
   constexpr int j = scan_coef(I);
-  const uint4 k = *reinterpret_cast<const uint4 *>(&rec[I]);  // c2, tmask, smask, off2 (broadcast)
-  const uint32_t sh = rec[I].shift;
+  const QuantRec k = rec[I];  // uniform: constant bank
   // lane = T + 16384.  Sign-magnitude rounding: (T + r - [T < 0]) >> s, and [T >= 0] is bit 14.
   const uint32_t z = x[j];
-  const uint32_t tz = (z >> 14) & k.y;
-  const uint32_t m = (((z + k.x + tz) >> sh) & k.z) + k.w;
-  const uint32_t ca = slut[m & 0xffffu], cb = slut[m >> 16];
+  const uint32_t tz = (z >> 14) & k.tmask;
+  const uint32_t zz = z + k.c2 + tz;
+  const uint32_t lo = (zz << 16) >> k.s16, hi = zz >> k.s16;  // = m + (16384 >> s) per lane
+  const uint32_t ca = slut[k.off + lo], cb = slut[k.off + hi];
   *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(ca | (cb << 8));
   dst += cols;
 }
@@ -176,25 +178,24 @@ __device__ __forceinline__ void quant_store(const uint32_t (&x)[64], const Quant
 }
 
 // grid (ceil(cols/tile_cols), ceil(rows/tile_rows), n), block 256.
-// dynamic smem: tile (tile_rows*8 pixel rows of tile_cols*8*NCH bytes) | quantiser records | LUT.
+// dynamic smem: LUT window | low-res corners | tile (tile_rows*8 pixel rows of tile_cols*8*NCH bytes).
 // The 8 warps of a CTA pass through the phases together (barriers at the phase boundaries): with
 // 2 CTAs per SM the live instruction window stays inside the instruction cache.
 template <int NCH, bool YCBCR>
 __global__ void __launch_bounds__(kFwd2Threads, 2)
     k_forward2(const uint8_t *__restrict__ pixels, const uint8_t *__restrict__ L, Geom g,
-               const __grid_constant__ Fwd2Params prm, const QuantPacked *__restrict__ qrecs,
-               const uint8_t *__restrict__ slut, uint8_t *__restrict__ planes) {
-  extern __shared__ __align__(128) uint8_t tile[];
+               const __grid_constant__ Fwd2Params prm, const uint8_t *__restrict__ slut,
+               uint8_t *__restrict__ planes) {
+  extern __shared__ __align__(128) uint8_t lut[];  // signed map LUT first: its address is a constant
   __shared__ uint64_t bar;
   const int pitch = prm.tile_cols * 8 * NCH;  // bytes per staged pixel row (multiple of 16)
   const int v0 = blockIdx.y * prm.tile_rows, u0 = blockIdx.x * prm.tile_cols;
   const int nblk = min(prm.tile_cols, g.cols - u0);  // even
   const int nrow = min(prm.tile_rows, g.rows - v0);
-  QuantRec *recs = reinterpret_cast<QuantRec *>(tile + (size_t)prm.tile_rows * 8 * pitch);
-  uint8_t *lut = reinterpret_cast<uint8_t *>(recs + 128);  // signed map LUT, 2*lut_half + 1 bytes
   // low-res samples needed by the tile: [NCH][tile_rows + 1][tile_cols + 2], edge clamped
   const int lw = prm.tile_cols + 2, lh = prm.tile_rows + 1;
   uint8_t *sL = lut + ((2 * prm.lut_half + 1 + 15) & ~15);
+  uint8_t *tile = sL + ((NCH * lh * lw + 127) & ~127);
   const uint8_t *img = pixels + (size_t)blockIdx.z * g.img_bytes;
 
   if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -205,10 +206,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 2)
     for (int y = 0; y < 8 * nrow; ++y)
       bulk_g2s(tile + y * pitch, img + ((size_t)(8 * v0 + y) * g.w + (size_t)u0 * 8) * NCH, row_bytes, &bar);
   }
-  {  // quantiser records and the needed window of the signed LUT, while the tile is in flight
-    const uint4 *qs = reinterpret_cast<const uint4 *>(qrecs);
-    for (int i = threadIdx.x; i < (int)(sizeof(QuantPacked) / 16); i += kFwd2Threads)
-      reinterpret_cast<uint4 *>(recs)[i] = __ldg(qs + i);
+  {  // the needed window of the signed LUT and the low-res corners, while the tile is in flight
     // lut_half is a multiple of 64 and the global table is padded: aligned 128-bit copies
     const int half = prm.lut_half, nv = (2 * half + 1 + 15) >> 4;
     const uint4 *src = reinterpret_cast<const uint4 *>(slut + (kLutCenter - half));
@@ -234,13 +232,15 @@ __global__ void __launch_bounds__(kFwd2Threads, 2)
     uint32_t x[64];
     __syncthreads();  // keep the CTA's warps in the same phase (instruction-cache locality)
     if (active) {
-      int cw0[4], cw1[4];
+      uint32_t cw0[4], cw1[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         cw0[k] = prm.cw[c].w0[k];
         cw1[k] = prm.cw[c].w1[k];
       }
-      const int cadd = prm.cw[c].add, cshr = prm.cw[c].shr;
+      const uint32_t cadd = prm.cw[c].add, csel = prm.cw[c].sel;
+      const uint32_t xm0 = prm.cw[c].xm[0], xm1 = prm.cw[c].xm[1], xm2 = prm.cw[c].xm[2];
+      const bool has_xm = prm.cw[c].has_xm != 0;
       // ---- low-res corners of both blocks (columns u, u+1, u+2; rows v, v+1), packed per lane
       uint32_t lf[9], rt[9];
       {
@@ -263,11 +263,15 @@ __global__ void __launch_bounds__(kFwd2Threads, 2)
           w[4 * k + 2] = q.z;
           w[4 * k + 3] = q.w;
         }
+        if (NCH > 1 && has_xm) {  // chroma: complement the G bytes
+#pragma unroll
+          for (int k = 0; k < 4 * NCH; ++k) w[k] ^= (k % 3 == 0) ? xm0 : (k % 3 == 1) ? xm1 : xm2;
+        }
         uint32_t t[9];
         nine2(lf[y], rt[y], t);
         const uint32_t *wa = w, *wb = w + 2 * NCH;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[y * 8 + i] = colour_pair<NCH>(wa, wb, i, cw0, cw1, cadd, cshr) - t[i] + 0x01000100u;
+        for (int i = 0; i < 8; ++i) x[y * 8 + i] = colour_pair<NCH>(wa, wb, i, cw0, cw1, cadd, csel) - t[i] + 0x01000100u;
         wht8p<256>(x[y * 8 + 0], x[y * 8 + 1], x[y * 8 + 2], x[y * 8 + 3], x[y * 8 + 4], x[y * 8 + 5], x[y * 8 + 6], x[y * 8 + 7]);
       }
       // ---- columns (bias 2048 -> 16384)
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(kFwd2Threads, 2)
     // ---- quantise both lanes, map, store the code pair
     if (active) {
       const int cls = (YCBCR && NCH >= 3 && (c == 1 || c == 2)) ? 1 : 0;
-      quant_store(x, recs + cls * 64, lut, seg + (size_t)c * g.cols * 64, g.cols, std::make_integer_sequence<int, 64>{});
+      quant_store(x, prm.rec[cls], lut, seg + (size_t)c * g.cols * 64, g.cols, std::make_integer_sequence<int, 64>{});
     }
   }
 }

@@ -432,14 +432,16 @@ def test_python_mirror_api(ctx, port):
 
 
 def test_host_batch_api_pipelined(ctx, port):
-    """himgcu_encode_batch_host / himgcu_decode_batch_host: pinned and pageable host buffers, several
-    sub-batches in flight (forced by a small staging budget), ragged last sub-batch."""
-    w, h, n, B = 256, 136, 3, 11
+    """himgcu_encode_batch_host / himgcu_decode_batch_host: pinned and pageable host buffers, more
+    sub-batches than coding lanes (forced by the smallest staging budget), ragged last sub-batch,
+    1 / 2 / 4 lanes."""
+    w, h, n, B = 256, 136, 3, 23
     imgs = np.stack([port.synth(w, h, n, 300 + k, 6) for k in range(B)])
     want = [port.encode(imgs[k], 80, True) for k in range(B)]
-    ctx.set_option("host_sub_batch_bytes", 3 * (w * h * n + 2 * 1024 * 1024))  # ~3 images per sub-batch
+    ctx.set_option("host_sub_batch_bytes", 1 << 20)  # 4-5 images per sub-batch
     try:
-        for pinned in (False, True):
+        for lanes, pinned in ((1, False), (2, True), (4, True), (4, False)):
+            ctx.set_option("host_lanes", lanes)
             src = torch.from_numpy(imgs).pin_memory() if pinned else imgs
             out, offsets, sizes = ctx.encode_batch_host(src, 80, True)
             out = np.asarray(out)
@@ -449,9 +451,10 @@ def test_host_batch_api_pipelined(ctx, port):
             px, status = ctx.decode_batch_host(out, offsets, sizes, w, h, n)
             assert int(np.abs(status).sum()) == 0
             for k in range(B):
-                assert_same(px[k], port.decode(want[k]), f"host batch decode {k}")
+                assert_same(px[k], port.decode(want[k]), f"host batch decode {k} ({lanes} lanes)")
     finally:
-        ctx.set_option("host_sub_batch_bytes", 256 << 20)
+        ctx.set_option("host_sub_batch_bytes", 64 << 20)
+        ctx.set_option("host_lanes", 3)
 
 
 def test_generic_kernels_still_match(port):
