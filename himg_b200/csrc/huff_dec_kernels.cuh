@@ -3,7 +3,7 @@
 // over-read (the reference's unchecked fast loop has undefined behaviour there).
 //
 //   k_dec_parse    one thread per image: RIFF/FRMT/LMAP/LRES/QCFG/FMAP/FRES walk + table recovery
-//   k_dec_tree     one CTA per chunk: serialised tree -> node arrays + 10-bit LUT
+//   k_dec_tree     one CTA per chunk: serialised tree -> node arrays + single- and multi-token LUTs
 //   k_dec_segtab   one thread per chunk: walk the 2/4-byte segment headers
 //   k_dec_stream   one thread per segment: LUT decode + tree walk for long codes + zero-run
 //                  expansion, 32-bit stores (the format's segments are independently decodable)
@@ -14,16 +14,19 @@
 
 namespace himgcu {
 
-constexpr int kLutBits = 10;
+#ifndef HIMG_DEC_LUT_BITS
+#define HIMG_DEC_LUT_BITS 11
+#endif
+constexpr int kLutBits = HIMG_DEC_LUT_BITS;
 constexpr int kLutSize = 1 << kLutBits;
 
-// Decode LUT entry (indexed by the next 10 stream bits, LSB first):
+// Decode LUT entry (indexed by the next kLutBits stream bits, LSB first):
 //   bits 0-7   literal byte (0 for zero-run tokens)
 //   bits 8-12  code length in bits (0 only for a single-leaf tree in strict mode)
 //   bits 13-16 number of extra bits that follow the code (0, 2, 4, 8 or 14)
 //   bits 17-25 run base: output bytes = base + extra  (1 for literals)
 //   bit 30     invalid slot (incomplete tree or symbol > 260)
-//   bit 31     code longer than 10 bits: bits 0-15 hold the tree node reached after 10 bits
+//   bit 31     code longer than kLutBits: bits 0-15 hold the tree node reached after kLutBits bits
 constexpr uint32_t kLutLong = 0x80000000u, kLutInvalid = 0x40000000u;
 
 __host__ __device__ inline uint32_t lut_entry(int sym, int len) {
@@ -44,10 +47,21 @@ struct ChunkDesc {
   uint32_t ok;
 };
 
+// Multi-token LUT entry (same index): every token that is completely determined by the 10 window
+// bits, up to two non-zero literals.
+// The last token of a group may be a zero run whose code lies in the window but whose extra bits do
+// not: they are then read from the bit buffer ("tail").
+//   x: bits 0-3 window bits consumed, 4-13 output bytes
+//      produced (without the tail's extra value), 14-17 tail extra bits (0 = none), 18-27 offset of
+//      the first non-zero literal
+//   y: bits 0-7 first non-zero literal, 8-17 offset of the second, 18-25 its value, 26-27 number of
+//      non-zero literals
+// No token (x bits 0-3 = 0): x = kLutLong | node << 4 (the first code is longer than the window; node
+// reached after kLutBits bits), kLutInvalid, or 0 (single-leaf tree).
 struct __align__(16) DecTree {
   uint32_t lut[kLutSize];  // see lut_entry()
-  short ca[kMaxNodes], cb[kMaxNodes], sym[kMaxNodes];
-  short pad;
+  uint2 lut2[kLutSize];
+  uint32_t nodes[kMaxNodes + 1];  // leaf: 0x80000000 | symbol; internal: child0 | child1 << 16 (0xffff = none)
   int nnodes;
   int data_off;  // first byte after the (byte-aligned) tree
   int ok;
@@ -251,9 +265,8 @@ __global__ void __launch_bounds__(kDecTreeThreads)
   }
   const bool single = n == 1;
   for (int k = t; k < n; k += blockDim.x) {
-    out->ca[k] = ca[k];
-    out->cb[k] = cb[k];
-    out->sym[k] = nsym[k];
+    out->nodes[k] = nsym[k] >= 0 ? (0x80000000u | (uint32_t)nsym[k])
+                                 : (((uint32_t)ca[k] & 0xffffu) | (((uint32_t)cb[k] & 0xffffu) << 16));
     const int dep = depth[k];
     if (nsym[k] >= 0) {
       if (dep <= kLutBits) {
@@ -272,6 +285,37 @@ __global__ void __launch_bounds__(kDecTreeThreads)
     out->nnodes = n;
     out->data_off = (s_bits + 7) >> 3;
     out->single = single ? 1 : 0;
+  }
+  __syncthreads();  // out->lut is complete (written by this CTA)
+  for (int p = t; p < kLutSize; p += blockDim.x) {
+    int pos = 0, bytes = 0, nlit = 0, tail = 0;
+    uint32_t off[2] = {0, 0}, lit[2] = {0, 0}, first = 0;
+    while (!single && pos < kLutBits) {
+      const uint32_t e = out->lut[(uint32_t)p >> pos];
+      if (e & (kLutLong | kLutInvalid)) {
+        if (pos == 0) first = (e & kLutInvalid) ? kLutInvalid : (kLutLong | ((e & 0xffffu) << 4));
+        break;
+      }
+      const int len = (int)((e >> 8) & 31u), nx = (int)((e >> 13) & 15u);
+      if (len == 0 || len > kLutBits - pos) break;  // the code is not determined by the window bits
+      if (len + nx > kLutBits - pos) {              // zero run with its extra bits beyond the window
+        bytes += (int)((e >> 17) & 511u);
+        pos += len;
+        tail = nx;
+        break;
+      }
+      const uint32_t l = e & 255u;
+      if (l) {
+        if (nlit == 2) break;
+        off[nlit] = (uint32_t)bytes;
+        lit[nlit] = l;
+        ++nlit;
+      }
+      bytes += (int)((e >> 17) & 511u) + (int)(((uint32_t)p >> (pos + len)) & ((1u << nx) - 1u));
+      pos += len + nx;
+    }
+    out->lut2[p] = make_uint2(first | (uint32_t)pos | ((uint32_t)bytes << 4) | ((uint32_t)tail << 14) | (off[0] << 18),
+                              lit[0] | (off[1] << 8) | (lit[1] << 18) | ((uint32_t)nlit << 26));
   }
 }
 
@@ -374,11 +418,12 @@ struct PBits {
     pos = bitpos;
   }
   __device__ __forceinline__ void refill() {
-    if (nb <= 32) {
-      buf |= (uint64_t)nxt << nb;
-      nb += 32;
-      nxt = ld(++widx);
-    }
+    // select-based: lanes of a warp refill at different times, a branch here diverges constantly
+    const bool r = nb <= 32;
+    buf |= r ? (uint64_t)nxt << (nb & 63) : 0ull;
+    nb += r ? 32 : 0;
+    widx += r ? 1u : 0u;
+    if (r) nxt = ld(widx);
   }
   __device__ __forceinline__ void consume(int n) {
     buf >>= n;
@@ -389,36 +434,42 @@ struct PBits {
 
 // Decodes one token.  Returns the number of output bytes it stands for (1 for a literal, the run
 // length for a zero-run token) or -1 on an invalid code; *lit receives the literal byte (0 for
-// runs).  After refill() at least 33 bits are buffered: enough for a 10-bit code + 14 extra bits.
-struct SNodes {
-  const short *ca, *cb, *sym;
-};
-__device__ __forceinline__ int decode_token(PBits &b, const uint32_t *lut, const SNodes &T, int *lit) {
-  b.refill();
-  uint32_t e = lut[(uint32_t)b.buf & (kLutSize - 1)];
-  if (e & (kLutLong | kLutInvalid)) {
-    if (e & kLutInvalid) return -1;
-    int node = (int)(e & 0xffffu), sym, guard = 0;
-    b.consume(kLutBits);
-    for (;;) {
-      sym = T.sym[node];
-      if (sym >= 0) break;
-      b.refill();
-      const int bit = (int)(b.buf & 1u);
-      b.consume(1);
-      node = bit ? T.cb[node] : T.ca[node];
-      if (node < 0 || ++guard > kMaxNodes) return -1;
-    }
-    e = lut_entry(sym, 0);
-    if (e & kLutInvalid) return -1;
-    b.refill();
-  }
+// runs).  After refill() at least 33 bits are buffered: enough for a kLutBits-bit code + 14 extra bits.
+// Finishes a token whose symbol is known: extra bits, run length.  Returns the output bytes.
+__device__ __forceinline__ int finish_token(PBits &b, uint32_t e, int *lit) {
   b.consume((int)((e >> 8) & 31u));
   const int nx = (int)((e >> 13) & 15u);
   const int z = (int)((e >> 17) & 511u) + (int)((uint32_t)b.buf & ((1u << nx) - 1u));
   b.consume(nx);
   *lit = (int)(e & 255u);
   return z;
+}
+// Token whose code is longer than the LUT window: walk the tree from `node` (reached after kLutBits
+// bits).  Returns the output bytes or -1.
+__device__ __forceinline__ int decode_long(PBits &b, const uint32_t *nodes, int node, int *lit) {
+  b.consume(kLutBits);
+  uint32_t w = nodes[node];
+  int guard = 0;
+  while (!(w & 0x80000000u)) {
+    b.refill();
+    const uint32_t child = (b.buf & 1u) ? (w >> 16) : (w & 0xffffu);
+    b.consume(1);
+    if (child >= (uint32_t)kMaxNodes || ++guard > kMaxNodes) return -1;
+    w = nodes[child];
+  }
+  const uint32_t e = lut_entry((int)(w & 0xffffu), 0);
+  if (e & kLutInvalid) return -1;
+  b.refill();
+  return finish_token(b, e, lit);
+}
+__device__ __forceinline__ int decode_token(PBits &b, const uint32_t *lut, const uint32_t *nodes, int *lit) {
+  b.refill();
+  const uint32_t e = __ldg(lut + ((uint32_t)b.buf & (kLutSize - 1)));
+  if (e & (kLutLong | kLutInvalid)) {
+    if (e & kLutInvalid) return -1;
+    return decode_long(b, nodes, (int)(e & 0xffffu), lit);
+  }
+  return finish_token(b, e, lit);
 }
 
 constexpr uint32_t kPosInvalid = 0xffffffffu;
@@ -438,8 +489,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
                                  const DecTree *__restrict__ trees, const SegRef *__restrict__ segs, int nseg,
                                  int out_seg, uint8_t *__restrict__ out, unsigned long long out_stride,
                                  int *__restrict__ status) {
-  __shared__ __align__(16) uint32_t lut[kLutSize];
-  __shared__ __align__(16) short s_nodes[3 * (kMaxNodes + 3)];
+  __shared__ __align__(16) uint2 lut2[kLutSize];  // the single-token LUT stays in global memory (rare path)
+  __shared__ uint32_t s_nodes[kMaxNodes + 1];
   __shared__ uint32_t s_end_all[WARP_TEAMS ? 32 * kParWarpTeams : kParMaxTeam];
   __shared__ uint32_t ws[33];
   __shared__ int s_flags[3 * (WARP_TEAMS ? kParWarpTeams : 1)];
@@ -453,15 +504,11 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   };
   const DecTree *T = trees + item;
   if (T->ok) {  // the whole CTA stages the image's LUT and tree
-    const uint4 *ls = reinterpret_cast<const uint4 *>(T->lut);
+    const uint4 *l2 = reinterpret_cast<const uint4 *>(T->lut2);
 #pragma unroll 4
-    for (int i = threadIdx.x; i < kLutSize / 4; i += blockDim.x) reinterpret_cast<uint4 *>(lut)[i] = __ldg(ls + i);
+    for (int i = threadIdx.x; i < kLutSize / 2; i += blockDim.x) reinterpret_cast<uint4 *>(lut2)[i] = __ldg(l2 + i);
     const int nn = T->nnodes;
-    for (int i = threadIdx.x; i < nn; i += blockDim.x) {
-      s_nodes[i] = T->ca[i];
-      s_nodes[(kMaxNodes + 3) + i] = T->cb[i];
-      s_nodes[2 * (kMaxNodes + 3) + i] = T->sym[i];
-    }
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) s_nodes[i] = T->nodes[i];
   }
   __syncthreads();
   if (WARP_TEAMS && b >= nseg) return;
@@ -472,7 +519,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   }
   uint32_t *s_end = s_end_all + 32 * tm;
   int &s_changed = s_flags[3 * tm], &s_bad = s_flags[3 * tm + 1], &s_final = s_flags[3 * tm + 2];
-  const SNodes SN{s_nodes, s_nodes + (kMaxNodes + 3), s_nodes + 2 * (kMaxNodes + 3)};
+  const uint32_t *SN = s_nodes;
+  const uint32_t *lut = T->lut;
   if (t == 0) s_bad = 0, s_final = -1;
   tsync();
   const uint8_t *src = data + cd[item].off + sr.off;
@@ -523,25 +571,81 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   const bool has_work = bound_lo < total_bits;
   uint32_t start = bound_lo, endpos = kPosInvalid, count = 0;
   bool dirty = has_work;
+  // Checkpoints of my previous decode: position of the first decode step at or after bound_lo + 64,
+  // 128, 256, 512 bits and the bytes counted before it.  A re-decode from a corrected start that
+  // lands on one of them continues exactly like the previous decode, so it stops there and
+  // splices the counts: the second round costs a few dozen bits instead of the whole subsequence.
+  constexpr int kCp = 4;
+  uint32_t cpp[kCp], cpc[kCp];
+#pragma unroll
+  for (int i = 0; i < kCp; ++i) cpp[i] = kPosInvalid, cpc[i] = 0;
   for (int round = 0; round <= team; ++round) {
     if (dirty) {
       PBits br;
       br.seek(src, sr.size, start);
-      count = 0;
-      endpos = kPosInvalid;
-      bool ok = true;
+      uint32_t cnt = 0, next_ms = bound_lo + 64u;
+      int mi = 0;
+      bool ok = true, spliced = false;
       while (br.pos < bound_hi) {
+        if (br.pos >= next_ms) {
+          uint32_t old_pos = kPosInvalid, old_cnt = 0;
+#pragma unroll
+          for (int i = 0; i < kCp; ++i)
+            if (i == mi) {
+              old_pos = cpp[i];
+              old_cnt = cpc[i];
+              cpp[i] = br.pos;
+              cpc[i] = cnt;
+            }
+          if (old_pos == br.pos) {
+            const uint32_t delta = cnt - old_cnt;
+#pragma unroll
+            for (int i = 0; i < kCp; ++i)
+              if (i > mi) cpc[i] += delta;
+            count += delta;  // endpos: as before
+            spliced = true;
+            break;
+          }
+          ++mi;
+          next_ms = mi < kCp ? bound_lo + (64u << mi) : 0xffffffffu;
+        }
+        br.refill();
+        // every token of the window starts in my range, and even a 14-bit tail ends inside the stream
+        if (br.pos + kLutBits <= bound_hi && br.pos + kLutBits + 14 <= total_bits) {
+          const uint32_t g = lut2[(uint32_t)br.buf & (kLutSize - 1)].x;
+          if (g & 15u) {
+            const int nb = (int)(g & 15u), nx = (int)((g >> 14) & 15u);
+            cnt += ((g >> 4) & 1023u) + ((uint32_t)(br.buf >> nb) & ((1u << nx) - 1u));
+            br.consume(nb + nx);
+            continue;
+          }
+          if (g & kLutLong) {  // code longer than the window: no second table lookup
+            int lit;
+            const int z = decode_long(br, SN, (int)((g >> 4) & 0xffffu), &lit);
+            if (z < 0 || br.pos > total_bits) {
+              ok = false;
+              break;
+            }
+            cnt += (uint32_t)z;
+            continue;
+          }
+        }
         int lit;
         const int z = decode_token(br, lut, SN, &lit);
         if (z < 0 || br.pos > total_bits) {
           ok = false;
           break;
         }
-        count += (uint32_t)z;
+        cnt += (uint32_t)z;
       }
-      // the last subsequence may run into the (possibly non-zero) padding bits: that is not an error
-      if (ok) endpos = br.pos;
-      else if (bound_hi == total_bits) endpos = total_bits;
+      if (!spliced) {
+        count = cnt;
+        // the last subsequence may run into the (possibly non-zero) padding bits: that is not an error
+        endpos = ok ? br.pos : (bound_hi == total_bits ? total_bits : kPosInvalid);
+#pragma unroll
+        for (int i = 0; i < kCp; ++i)
+          if (i >= mi) cpp[i] = kPosInvalid;
+      }
     }
     s_end[t] = has_work ? endpos : kPosInvalid;
     if (t == 0) s_changed = 0;
@@ -556,6 +660,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
         if (!dirty) {
           count = 0;
           endpos = start;  // nothing starts in my range: pass the position through
+#pragma unroll
+          for (int i = 0; i < kCp; ++i) cpp[i] = kPosInvalid;
         }
         s_changed = 1;
       }
@@ -595,8 +701,26 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
     int n = (int)off;
     bool ok = true;
     while (br.pos < bound_hi && n < out_seg) {
+      br.refill();
+      int long_node = -1;
+      if (br.pos + kLutBits <= bound_hi && br.pos + kLutBits + 14 <= total_bits) {
+        const uint2 g = lut2[(uint32_t)br.buf & (kLutSize - 1)];
+        const int nb = (int)(g.x & 15u), nx = (int)((g.x >> 14) & 15u);
+        const int gb = (int)((g.x >> 4) & 1023u) + (int)((uint32_t)(br.buf >> nb) & ((1u << nx) - 1u));
+        if (nb && n + gb <= out_seg) {  // the whole group lies inside the segment
+          if (g.y >> 26) {
+            o[n + (int)((g.x >> 18) & 1023u)] = (uint8_t)g.y;
+            if ((g.y >> 26) > 1) o[n + (int)((g.y >> 8) & 1023u)] = (uint8_t)(g.y >> 18);
+          }
+          br.consume(nb + nx);
+          n += gb;
+          if (n == out_seg) s_final = (int)br.pos;
+          continue;
+        }
+        if (!nb && (g.x & kLutLong)) long_node = (int)((g.x >> 4) & 0xffffu);
+      }
       int lit;
-      const int z = decode_token(br, lut, SN, &lit);
+      const int z = long_node >= 0 ? decode_long(br, SN, long_node, &lit) : decode_token(br, lut, SN, &lit);
       if (z < 0 || br.pos > total_bits || n + z > out_seg) {
         ok = false;  // a zero run that overshoots the segment is an error (huffman_dec.cpp:352)
         break;
