@@ -549,7 +549,7 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
       LAUNCH("k_huff_pack", k_huff_pack, grid, kHuffThreads, win_bytes, chunks[k].d_in, hg, d_trees[k], d_bits[k],
              d_pos[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
     else
-      LAUNCH("k_huff_pack", k_huff_pack2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_trees[k], d_bits[k], d_pos[k],
+      LAUNCH("k_huff_pack", k_huff_pack3, grid, kTokThreads, 0, chunks[k].d_in, hg, d_trees[k], d_bits[k], d_pos[k],
              d_sizes, d_out, (unsigned long long)out_stride, d_err);
     if (hg.nseg > 1) {
       const long long tot = (long long)n * hg.nseg;

@@ -698,37 +698,35 @@ __global__ void __launch_bounds__(kHuffThreads)
   }
 }
 
-// ---- K-pack v2 (balanced) --------------------------------------------------------------------
-constexpr int kWin2Words = 4096;  // 16 KiB bit window + 2 words of slack
+// ---- K-pack (balanced) -----------------------------------------------------------------------
+constexpr int kWin2Words = 4096;  // 16 KiB bit window + slack words
 constexpr int kWin2Bits = kWin2Words * 32;
 
-struct PackTables {
-  const uint32_t *code;
-  const uint8_t *len;
-  const uint32_t *lenx;  // len + extra bits
-};
+// Balanced item list as in k_huff_hist2; a thread takes EIGHT CONSECUTIVE items of a round of 2048,
+// builds their tokens once ([zero-run token][literal code], usually < 16 bits per item) and keeps
+// them in registers; one block scan of the per-thread bit totals gives its position, and the bits
+// go into the window through a 64-bit register accumulator, one atomicOr per 32-bit WORD instead
+// of up to three per token.  The window is flushed only when the next round would not fit.
+constexpr int kP3Items = 8;
+constexpr int kP3Round = kTokThreads * kP3Items;
 
-__device__ __forceinline__ uint32_t item_bits(const PackTables &T, uint32_t gap, uint32_t byte) {
-  uint32_t bits = T.len[byte];
-  if (gap) {
-    if (gap >= (uint32_t)kMaxRun) {
-      const uint32_t nfull = gap / kMaxRun;
-      bits += nfull * T.lenx[260];
-      gap -= nfull * kMaxRun;
-    }
-    if (gap) {
-      uint32_t ex;
-      bits += T.lenx[run_symbol(gap, &ex)];
-    }
-  }
-  return bits;
+// zero run of z (1 <= z < kMaxRun) bytes -> token value and length; tab[s] = {code, len | lenx << 8}
+__device__ __forceinline__ void run_token(const uint2 *tab, uint32_t z, uint64_t *tok, uint32_t *bits) {
+  int sym = 260;
+  uint32_t base = 279;
+  if (z <= 278) sym = 259, base = 23;
+  if (z <= 22) sym = 258, base = 7;
+  if (z <= 6) sym = 257, base = 3;
+  if (z <= 2) sym = z == 1 ? 0 : 256, base = z;
+  const uint2 r = tab[sym];
+  *tok = (uint64_t)r.x | ((uint64_t)(z - base) << (r.y & 255u));
+  *bits = r.y >> 8;
 }
 
-// ORs `n` (<= 46) bits of `val` into the window at bit position `pos` if the token STARTS inside
-// the window [w0, w0 + kWin2Bits); it may spill into the two slack words.
-__device__ __forceinline__ void put_token(uint32_t *win, uint32_t pos, uint32_t w0, uint64_t val, int n) {
-  if (n == 0 || pos < w0 || pos >= w0 + (uint32_t)kWin2Bits) return;
-  const uint32_t rel = pos - w0, word = rel >> 5, sh = rel & 31;
+// ORs n (<= 64) bits into the window at bit position pos (two slack words behind the window)
+__device__ __forceinline__ void put64(uint32_t *win, uint32_t pos, uint64_t val, uint32_t n) {
+  if (n == 0) return;
+  const uint32_t word = pos >> 5, sh = pos & 31;
   const uint64_t v0 = val << sh;
   const uint32_t lo = (uint32_t)v0, mid = (uint32_t)(v0 >> 32), hi = sh ? (uint32_t)(val >> (64 - sh)) : 0u;
   if (lo) atomicOr(&win[word], lo);
@@ -736,128 +734,186 @@ __device__ __forceinline__ void put_token(uint32_t *win, uint32_t pos, uint32_t 
   if (hi) atomicOr(&win[word + 2], hi);
 }
 
-// Emits the zero-run tokens of `gap` zeros starting at bit position `pos`; returns the new position.
-__device__ __forceinline__ uint32_t emit_run_tokens(uint32_t *win, uint32_t pos, uint32_t w0, const PackTables &T, uint32_t gap) {
-  while (gap >= (uint32_t)kMaxRun) {
-    put_token(win, pos, w0, (uint64_t)T.code[260] | ((uint64_t)(kMaxRun - 279) << T.len[260]), (int)T.lenx[260]);
-    pos += T.lenx[260];
-    gap -= kMaxRun;
-  }
-  if (gap) {
-    uint32_t ex;
-    const int sym = run_symbol(gap, &ex);
-    put_token(win, pos, w0, (uint64_t)T.code[sym] | ((uint64_t)ex << T.len[sym]), (int)T.lenx[sym]);
-    pos += T.lenx[sym];
-  }
-  return pos;
-}
-
 // grid (nseg, n), block kTokThreads.
 __global__ void __launch_bounds__(kTokThreads)
-    k_huff_pack2(const uint8_t *__restrict__ in, HuffGeom hg, const TreeOut *__restrict__ trees,
+    k_huff_pack3(const uint8_t *__restrict__ in, HuffGeom hg, const TreeOut *__restrict__ trees,
                  const uint32_t *__restrict__ seg_bits, const uint32_t *__restrict__ seg_pos,
                  const uint32_t *__restrict__ sizes, uint8_t *__restrict__ out, unsigned long long out_stride,
                  int *err) {
   __shared__ uint32_t win[kWin2Words + 4];
-  __shared__ uint32_t s_code[kSyms];
-  __shared__ uint8_t s_len[kSyms + 3];
-  __shared__ uint32_t s_lenx[kSyms];
+  __shared__ uint2 s_tab[kSyms];
   __shared__ uint32_t ws[kTokWarps + 1];
-  __shared__ uint32_t s_wbits[kTokWarps];
+  __shared__ uint32_t s_half;
   __shared__ uint32_t rows[kTokThreads * kRowWords];
-  __shared__ unsigned short ipos[kTokPiece];
-  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ __align__(16) unsigned short ipos[kTokPiece + 8];
+  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
   if (sizes[item] == 0) return;  // did not fit (k_huff_layout)
   const TreeOut *tr = trees + item;
   for (int s = t; s < kSyms; s += blockDim.x) {
-    s_code[s] = tr->code[s];
-    s_len[s] = tr->len[s];
-    s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+    const uint32_t l = tr->len[s];
+    s_tab[s] = make_uint2(tr->code[s], l | ((l + (uint32_t)sym_extra_bits(s)) << 8));
   }
   for (int i = t; i < kWin2Words + 4; i += blockDim.x) win[i] = 0;
   __syncthreads();
-  const PackTables T{s_code, s_len, s_lenx};
   const uint8_t *seg = in + (size_t)item * hg.in_stride + (size_t)b * hg.seg_size;
   uint8_t *dst = out + (size_t)item * out_stride + seg_pos[(size_t)item * hg.nseg + b];
+  const uint32_t full_bits = s_tab[260].y >> 8;  // one maximal run token
+  const uint64_t full_tok = (uint64_t)s_tab[260].x | ((uint64_t)(kMaxRun - 279) << (s_tab[260].y & 255u));
 
   uint32_t carry = 0;  // zeros of the run that is still open
-  uint32_t gbits = 0;  // bits emitted so far; complete bytes below gbits>>3 are already in `dst`
+  uint32_t gbyte = 0;  // complete bytes already written to dst
+  uint32_t wfill = 0;  // bits in the window; window bit 0 = bit 0 of byte gbyte
+  // Writes the complete bytes of the window to dst and keeps the unfinished byte.  Uniform call.
+  auto flush = [&]() {
+    __syncthreads();
+    const uint32_t nbytes = wfill >> 3;
+    const uint8_t *wb = reinterpret_cast<const uint8_t *>(win);
+    uint8_t *o = dst + gbyte;
+    for (uint32_t i = t; i < nbytes; i += kTokThreads) o[i] = wb[i];
+    const uint32_t keep = (wfill & 7) ? wb[nbytes] : 0u;
+    __syncthreads();
+    const uint32_t used = min((wfill >> 5) + 4u, (uint32_t)(kWin2Words + 4));
+    for (uint32_t i = t; i < used; i += kTokThreads) win[i] = i == 0 ? keep : 0u;
+    __syncthreads();
+    gbyte += nbytes;
+    wfill &= 7;
+  };
+  // nfull maximal run tokens (16662 zeros each), cut greedily from the start of a run.  Uniform call.
+  auto emit_full_runs = [&](uint32_t nfull) {
+    while (nfull) {
+      const uint32_t cap = ((uint32_t)kWin2Bits - wfill) / full_bits;
+      if (cap == 0) {
+        flush();
+        continue;
+      }
+      const uint32_t n = min(nfull, cap);
+      if (t == 0)
+        for (uint32_t i = 0; i < n; ++i) put64(win, wfill + i * full_bits, full_tok, full_bits);
+      wfill += n * full_bits;
+      nfull -= n;
+    }
+  };
+
   for (int base = 0; base < hg.seg_size; base += kTokPiece) {
     PieceItems P;
-    const uint32_t carry_out = build_items(seg, hg.seg_size, base, rows, ipos, ws, carry, &P);
-    carry = carry_out;
-    const bool last_piece = base + kTokPiece >= hg.seg_size;
-    // ---- pass 1: bit total of every warp's item range (ranges are multiples of 32 items)
-    const int per = ((P.count + kTokThreads - 1) / kTokThreads) * 32;
-    const int k0 = warp * per, k1 = min(k0 + per, P.count);
-    uint32_t bits = 0;
-    for (int k = k0 + lane; k < k1; k += 32) bits += item_bits(T, item_gap(ipos, k, P.zeros_in), item_byte(rows, ipos[k]));
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
-    if (lane == 0) s_wbits[warp] = bits;
-    __syncthreads();
-    uint32_t wbase = 0, piece_bits = 0;
-#pragma unroll
-    for (int w = 0; w < kTokWarps; ++w) {
-      if (w < warp) wbase += s_wbits[w];
-      piece_bits += s_wbits[w];
-    }
-    // the run still open at the segment end is one more (item-less) token group
-    const uint32_t tail_gap = (last_piece ? carry_out : 0u);
-    const uint32_t items_bits = piece_bits;
-    if (tail_gap) piece_bits += item_bits(T, tail_gap, 0) - T.len[0];
-    // ---- pass 2: emit through the bit window; window bit 0 = byte boundary at or below gbits
-    const uint32_t lead = gbits & 7, vend = lead + piece_bits, gbyte = gbits >> 3;
-    for (uint32_t w0 = 0; w0 < vend || w0 == 0; w0 += kWin2Bits) {
-      uint32_t running = lead + wbase;
-      for (int kk = k0; kk < k1; kk += 32) {
-        const int k = kk + lane;
-        uint32_t gap = 0, byte = 0, nb = 0;
-        if (k < k1) {
-          gap = item_gap(ipos, k, P.zeros_in);
-          byte = item_byte(rows, ipos[k]);
-          nb = item_bits(T, gap, byte);
-        }
-        uint32_t inc = nb;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += v;
-        }
-        if (k < k1) {
-          uint32_t pos = running + inc - nb;
-          pos = emit_run_tokens(win, pos, w0, T, gap);
-          put_token(win, pos, w0, T.code[byte], T.len[byte]);
-        }
-        running += __shfl_sync(0xffffffffu, inc, 31);
+    carry = build_items(seg, hg.seg_size, base, rows, ipos, ws, carry, &P);
+    // a first gap of 16662 zeros or more: its maximal tokens go out first, the remainder stays with item 0
+    uint32_t gap0_cut = 0;
+    if (P.count > 0) {
+      const uint32_t gap0 = (uint32_t)ipos[0] + P.zeros_in;
+      if (gap0 >= (uint32_t)kMaxRun) {
+        gap0_cut = (gap0 / kMaxRun) * kMaxRun;
+        emit_full_runs(gap0 / kMaxRun);
       }
-      if (t == 0 && tail_gap) emit_run_tokens(win, lead + items_bits, w0, T, tail_gap);
-      __syncthreads();
-      const bool last_win = w0 + (uint32_t)kWin2Bits >= vend;
-      const uint32_t nbytes = last_win ? ((vend - w0) >> 3) : (uint32_t)(kWin2Bits / 8);
-      const uint8_t *wb = reinterpret_cast<const uint8_t *>(win);
-      uint8_t *o = dst + gbyte + (w0 >> 3);
-      for (uint32_t i = t; i < nbytes; i += blockDim.x) o[i] = wb[i];
-      __syncthreads();
-      // carry the unfinished tail (partial byte, or the slack words) to the front of the window
-      uint32_t c0 = 0, c1 = 0;
-      if (last_win) {
-        c0 = ((vend - w0) & 7) ? wb[nbytes] : 0;
-      } else {
-        c0 = win[kWin2Words];
-        c1 = win[kWin2Words + 1];
-      }
-      __syncthreads();
-      const int used = last_win ? (int)((vend - w0 + 31) >> 5) + 3 : kWin2Words + 4;
-      for (int i = t; i < min(used, kWin2Words + 4); i += blockDim.x) win[i] = i == 0 ? c0 : (i == 1 ? c1 : 0u);
-      __syncthreads();
-      if (last_win) break;
     }
-    gbits += piece_bits;
+    for (int r0 = 0; r0 < P.count; r0 += kP3Round) {
+      const int k0 = r0 + t * kP3Items;
+      const int m = min(max(P.count - k0, 0), kP3Items);
+      uint64_t tok[kP3Items];
+      uint32_t tl[kP3Items];
+      uint32_t tbits = 0;
+      bool wide = false;  // an item of more than 32 bits: this thread bypasses the accumulator
+      if (m > 0) {
+        const uint4 pv = *reinterpret_cast<const uint4 *>(ipos + k0);
+        const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
+        int prev = k0 ? (int)ipos[k0 - 1] : -1;
+#pragma unroll
+        for (int j = 0; j < kP3Items; ++j) {
+          tok[j] = 0;
+          tl[j] = 0;
+          if (j < m) {
+            const int pos = (int)((pw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+            uint32_t gap = (uint32_t)(pos - prev - 1);
+            if (k0 + j == 0) gap += P.zeros_in - gap0_cut;
+            prev = pos;
+            const uint2 lr = s_tab[item_byte(rows, pos)];
+            uint64_t tk = lr.x;
+            uint32_t l = lr.y & 255u;
+            if (gap) {
+              uint64_t rt;
+              uint32_t rb;
+              run_token(s_tab, gap, &rt, &rb);
+              tk = rb + l <= 64 ? (rt | (tk << rb)) : rt;  // > 64 bits: the run token alone, literal re-read later
+              l += rb;
+            }
+            wide |= l > 32;
+            tok[j] = tk;
+            tl[j] = l;
+            tbits += l;
+          }
+        }
+      }
+      uint32_t total;
+      const uint32_t tb = block_exscan_u32(tbits, ws, &total);
+      if (wfill + total > (uint32_t)kWin2Bits) flush();
+      // A round of incompressible data may not fit even the empty window: two halves then.
+      const bool split = wfill + total > (uint32_t)kWin2Bits;
+      if (split) {
+        if (t == kTokThreads / 2) s_half = tb;
+        __syncthreads();
+      }
+      const uint32_t half0 = split ? s_half : total;
+      for (int hlf = 0; hlf < (split ? 2 : 1); ++hlf) {
+        if (hlf == 1) flush();
+        const bool mine = !split || (t >= kTokThreads / 2) == (hlf == 1);
+        const uint32_t rel = hlf == 1 ? tb - half0 : tb;
+        if (mine && m > 0) {
+          uint32_t pos = wfill + rel;
+          if (!wide) {
+            uint32_t word = pos >> 5, fill = pos & 31;
+            uint64_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < kP3Items; ++j) {
+              acc |= tok[j] << fill;  // tl <= 32 and fill < 32
+              fill += tl[j];
+              if (fill >= 32) {
+                atomicOr(&win[word], (uint32_t)acc);
+                acc >>= 32;
+                fill -= 32;
+                ++word;
+              }
+            }
+            if ((uint32_t)acc) atomicOr(&win[word], (uint32_t)acc);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kP3Items; ++j) {
+              if (j < m) {
+                if (tl[j] <= 64) {
+                  put64(win, pos, tok[j], tl[j]);
+                } else {  // run token, then the literal
+                  const uint2 lr = s_tab[item_byte(rows, (int)ipos[k0 + j])];
+                  const uint32_t rb = tl[j] - (lr.y & 255u);
+                  put64(win, pos, tok[j], rb);
+                  put64(win, pos + rb, lr.x, lr.y & 255u);
+                }
+                pos += tl[j];
+              }
+            }
+          }
+        }
+        wfill += hlf == 1 ? total - half0 : half0;
+      }
+    }
+    __syncthreads();  // rows / ipos are rewritten by the next piece
   }
+  // the run still open at the segment end
+  if (carry) {
+    emit_full_runs(carry / kMaxRun);
+    const uint32_t rest = carry % kMaxRun;
+    if (rest) {
+      uint64_t rt;
+      uint32_t rb;
+      run_token(s_tab, rest, &rt, &rb);
+      if (wfill + rb > (uint32_t)kWin2Bits) flush();
+      if (t == 0) put64(win, wfill, rt, rb);
+      wfill += rb;
+    }
+  }
+  flush();
   // final partial byte (its padding bits are zero here; k_huff_stale adds the stale ones)
   if (t == 0) {
-    if (gbits & 7) dst[gbits >> 3] = (uint8_t)win[0];
+    const uint32_t gbits = gbyte * 8u + wfill;
+    if (wfill) dst[gbyte] = (uint8_t)win[0];
     if (gbits != seg_bits[(size_t)item * hg.nseg + b]) atomicMax(err, 99);  // internal consistency
   }
 }

@@ -140,6 +140,20 @@ def _huff_cases():
     z[[19999, 39998]] = 5
     cases += [(z, 0), (z, 20000), (np.zeros(50000, np.uint8), 0), (np.zeros(50000, np.uint8), 10000),
               (np.full(5000, 7, np.uint8), 0), (np.full(5000, 7, np.uint8), 1000)]
+    # Fibonacci symbol counts 1, 1, 2, 3, 5, ... over {literal 24, run symbol 260, run symbol 259, literals
+    # 23 .. 1}: codes of up to 26 bits.  "5000 zeros + literal 24" is one item of 40 + 26 bits (> 64),
+    # "100 zeros + literal 23" one of 33 + 24 bits (> 32): the wide-item paths of the packer and the
+    # tree walk of the decoder.
+    f = [1, 1]
+    while len(f) < 27:
+        f.append(f[-1] + f[-2])
+    dense = np.concatenate([np.full(f[26 - k] - (2 if k == 22 else 0), k + 1, np.uint8) for k in range(23)])  # literals 1..23
+    rng.shuffle(dense)
+    z = lambda n, v: np.r_[np.zeros(n, np.uint8), np.uint8(v)]
+    deep = np.concatenate([dense[:1000], [np.uint8(25)], dense[1000:70001], z(5000, 24), dense[70001:300000], z(100, 23), dense[300000:300007], z(200, 23),
+                           dense[300007:]])
+    deep = deep[: deep.size & ~3]
+    cases += [(deep, 0)]
     return cases
 
 
