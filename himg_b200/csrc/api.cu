@@ -20,6 +20,7 @@
 #include "tables.h"
 #include "xform_fwd2.cuh"
 #include "xform_inv2.cuh"
+#include "xform_inv3.cuh"
 #include "xform_kernels.cuh"
 
 using namespace himgcu;
@@ -452,8 +453,37 @@ int launch_inv2(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, in
   return HIMGCU_OK;
 }
 
+template <int NCH, int PITCH>
+int launch_inv3(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
+                const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  // balanced column tiles of at most PITCH blocks, multiples of 16 blocks; 512 / PITCH block rows per tile
+  const int nt = (g.cols + PITCH - 1) / PITCH;
+  const int tile_cols = std::min(PITCH, (((g.cols + nt - 1) / nt) + 15) & ~15);
+  constexpr int trows = 512 / PITCH;
+  dim3 grid((g.cols + tile_cols - 1) / tile_cols, (g.rows + trows - 1) / trows, n);
+  const int smem = trows * NCH * 64 * PITCH + 16 * 256 * 2;
+  CK(cudaFuncSetAttribute((k_inverse3<NCH, PITCH>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  LAUNCH("k_inverse", (k_inverse3<NCH, PITCH>), grid, kInv3Threads, smem, d_planes, d_R, g, d_tabs, tab_stride, tile_cols,
+         d_pixels);
+  return HIMGCU_OK;
+}
+
+template <int NCH>
+int launch_inv3_any(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
+                    const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  if (g.cols > 128) return launch_inv3<NCH, 256>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+  if (g.cols > 64) return launch_inv3<NCH, 128>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+  return launch_inv3<NCH, 64>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+}
+
 int stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
                   const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  // lane-pair fast path: two blocks per thread, 16-byte pixel stores
+  if (!ctx->force_generic && (g.h % 8) == 0 && (g.cols % 16) == 0 && (g.w % 16) == 0 && (g.nch == 1 || g.nch == 3) &&
+      (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0) {
+    if (g.nch == 1) return launch_inv3_any<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    return launch_inv3_any<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+  }
   if (!ctx->force_generic && (g.w % 8) == 0 && (g.h % 8) == 0 && (g.cols % 16) == 0 &&
       (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pixels) & 7) == 0 &&
       (((size_t)g.w * g.nch) & 7) == 0) {

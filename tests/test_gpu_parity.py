@@ -314,6 +314,36 @@ def test_stage_inverse_random_planes(ctx, port, shape):
         assert_same(got, want, f"inverse {shape} q{q} ycbcr={yc}")
 
 
+@pytest.mark.parametrize("shape", [(128, 16, 3), (256, 24, 1), (640, 48, 3), (2176, 16, 3), (1920, 24, 3), (1024, 40, 1),
+                                   (4224, 8, 3)])
+@pytest.mark.parametrize("kind", ["small", "mixed", "wild"])
+def test_stage_inverse_lane_pair_path(ctx, port, shape, kind):
+    """Shapes that take the two-blocks-per-thread kernel (cols % 16 == 0): one, two and ragged tile
+    rows, several column tiles.  'small' keeps every coefficient inside [-4096, 4095] (packed 16-bit
+    arithmetic), 'wild' is random code bytes (every warp falls back to the int32 arithmetic),
+    'mixed' has a few large codes so both paths run side by side in one launch."""
+    w, h, n = shape
+    rng = np.random.default_rng(w + 31 * h + len(kind))
+    rows, cols = h >> 3, w >> 3
+    size = rows * cols * 64 * n
+    if kind == "wild":
+        planes = rng.integers(0, 256, size, dtype=np.uint8)
+        planes[rng.random(size) < 0.5] = 0
+    else:
+        planes = rng.choice(np.array([0, 0, 0, 0, 1, 255, 2, 254, 3, 253, 9, 247, 30, 226], np.uint8), size)
+        if kind == "mixed":
+            idx = rng.integers(0, size, max(1, size // 3000))
+            planes[idx] = rng.integers(100, 157, idx.size, dtype=np.uint8)
+    R = rng.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+    unmap = port.mapfun_parse(port.mapfun_serialize(port.fullres_map_table()))
+    for q, yc in ((50, True), (100, False), (0, True)):
+        yc = yc and n >= 3
+        sl, sc = port.shift_table(q, 0), port.shift_table(q, 1)
+        want = port.fullres_restore(planes, w, h, n, yc, R, sl, sc, unmap)
+        got = ctx.stage_inverse(dev(planes[None]), dev(R[None]), w, h, n, yc, sl, sc, unmap).cpu().numpy()[0]
+        assert_same(got, want, f"inverse {shape} {kind} q{q} ycbcr={yc}")
+
+
 # ---------------------------------------------------------------------------------------------
 # whole decoder
 # ---------------------------------------------------------------------------------------------
