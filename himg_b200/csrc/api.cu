@@ -542,22 +542,37 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   size_t prefix_off = 0;
   TreeOut *d_trees[2];
   uint32_t *d_seghist[2], *d_bits[2], *d_pos[2];
+  uint32_t *d_part[2];
   for (int k = 0; k < nchunks; ++k) {
-    const HuffGeom &hg = chunks[k].hg;
+    HuffGeom &hg = chunks[k].hg;
+    // Parts per segment: only worth it when the segments alone cannot fill the GPU (single images:
+    // the whole low-res chunk is ONE unframed segment).  Target ~2 CTAs per SM, parts of >= 8 KiB.
+    hg.nsub = 1;
+    hg.sub_size = hg.seg_size;
+    const long long ctas = (long long)n * hg.nseg;
+    if (!ctx->force_generic && ctas < 296 && hg.seg_size > 2 * kTokPiece) {
+      const int want = (int)std::min<long long>(64, (296 + ctas - 1) / ctas);
+      const int sub = (int)((((long long)hg.seg_size + want - 1) / want + kTokPiece - 1) / kTokPiece) * kTokPiece;
+      hg.sub_size = sub;
+      hg.nsub = (hg.seg_size + sub - 1) / sub;
+    }
     const std::string tag = chunks[k].tag;
-    ENSURE((tag + "_seghist").c_str(), (size_t)n * hg.nseg * kSyms * sizeof(uint32_t), d_seghist[k]);
+    ENSURE((tag + "_seghist").c_str(), (size_t)n * hg.nseg * hg.nsub * kSyms * sizeof(uint32_t), d_seghist[k]);
+    ENSURE((tag + "_partstart").c_str(), (size_t)n * hg.nseg * hg.nsub * sizeof(uint32_t), d_part[k]);
     ENSURE((tag + "_trees").c_str(), (size_t)n * sizeof(TreeOut), d_trees[k]);
     ENSURE((tag + "_segbits").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_bits[k]);
     ENSURE((tag + "_segpos").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_pos[k]);
-    dim3 grid(hg.nseg, n);
+    dim3 grid(hg.nseg * hg.nsub, n);
     if (ctx->force_generic) LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
     else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
-    LAUNCH("k_huff_tree", k_huff_tree, n, kTreeThreads, 0, d_seghist[k], hg.nseg, d_trees[k], d_err);
+    LAUNCH("k_huff_tree", k_huff_tree, n, kTreeThreads, 0, d_seghist[k], hg.nseg * hg.nsub, d_trees[k], d_err);
     LayoutChunk &C = P.ch[k];
     C.seghist = d_seghist[k];
     C.trees = d_trees[k];
     C.seg_bits = d_bits[k];
     C.seg_pos = d_pos[k];
+    C.part_start = d_part[k];
+    C.nsub = hg.nsub;
     C.prefix = chunks[k].prefix.empty() ? nullptr : d_prefix + prefix_off;
     C.prefix_len = (int)chunks[k].prefix.size();
     C.size_patch = chunks[k].size_patch;
@@ -574,13 +589,13 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   }
   for (int k = 0; k < nchunks; ++k) {
     const HuffGeom &hg = chunks[k].hg;
-    dim3 grid(hg.nseg, n);
+    dim3 grid(hg.nseg * hg.nsub, n);
     if (ctx->force_generic)
       LAUNCH("k_huff_pack", k_huff_pack, grid, kHuffThreads, win_bytes, chunks[k].d_in, hg, d_trees[k], d_bits[k],
              d_pos[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
     else
       LAUNCH("k_huff_pack", k_huff_pack3, grid, kTokThreads, 0, chunks[k].d_in, hg, d_trees[k], d_bits[k], d_pos[k],
-             d_sizes, d_out, (unsigned long long)out_stride, d_err);
+             d_part[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
     if (hg.nseg > 1) {
       const long long tot = (long long)n * hg.nseg;
       LAUNCH("k_huff_stale", k_huff_stale, (unsigned)((tot + 255) / 256), 256, 0, n, hg.nseg, d_bits[k], d_pos[k],
@@ -622,12 +637,12 @@ int encode_device(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g
   if (rc) return rc;
   HuffChunkArgs ch[2];
   ch[0].d_in = d_lres;
-  ch[0].hg = HuffGeom{g.lres_size, g.lres_size, 1, g.lres_stride};
+  ch[0].hg = HuffGeom{g.lres_size, g.lres_size, 1, g.lres_stride, 1, g.lres_size};
   ch[0].tag = "lres";
   ch[0].prefix = ct.head;
   ch[0].size_patch = (int)ct.head.size() - 4;
   ch[1].d_in = d_planes;
-  ch[1].hg = HuffGeom{(int)g.planes_bytes, g.seg, g.rows, g.planes_bytes};
+  ch[1].hg = HuffGeom{(int)g.planes_bytes, g.seg, g.rows, g.planes_bytes, 1, g.seg};
   ch[1].tag = "fres";
   ch[1].prefix = ct.mid;
   ch[1].size_patch = (int)ct.mid.size() - 4;
@@ -1297,7 +1312,7 @@ int himgcu_stage_huff_compress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in_s
   CK(cudaSetDevice(ctx->device));
   HuffChunkArgs ch;
   ch.d_in = d_in;
-  ch.hg = HuffGeom{in_size, block_size, in_size / block_size, (unsigned long long)in_stride};
+  ch.hg = HuffGeom{in_size, block_size, in_size / block_size, (unsigned long long)in_stride, 1, block_size};
   ch.tag = "stage";
   ch.size_patch = -1;
   return huff_encode_items(ctx, n, &ch, 1, false, d_out, out_stride, d_sizes);

@@ -31,6 +31,11 @@ struct HuffGeom {
   int seg_size;  // bytes per segment (== in_size when the chunk is unframed)
   int nseg;
   unsigned long long in_stride;  // bytes between the chunks of consecutive items
+  // A segment may be coded by `nsub` CTAs, each taking `sub_size` bytes (a multiple of the 8 KiB
+  // piece): the segment stays ONE bit stream; the parts meet at arbitrary bit positions.  Used for
+  // the single unframed low-res stream of large images when the batch alone cannot fill the GPU.
+  int nsub;
+  int sub_size;
 };
 
 struct TreeOut {
@@ -257,20 +262,56 @@ __device__ __forceinline__ int run_symbol(uint32_t z, uint32_t *extra) {
   return 260;
 }
 
-// grid (nseg, n), block kTokThreads.  seghist: [n][nseg][261].
+// Number of zero bytes immediately before byte `pos` of a segment (block-cooperative, uniform
+// result): the run that is open where a part starts.  Usually one 2 KiB look-back.
+__device__ __forceinline__ uint32_t zeros_before(const uint8_t *__restrict__ seg, int pos, int *s_last) {
+  uint32_t zeros = 0;
+  int end = pos;
+  while (end > 0) {
+    const int win = min(end, kTokThreads * 8), start = end - win;
+    if (threadIdx.x == 0) *s_last = -1;
+    __syncthreads();
+    int last = -1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = start + 8 * (int)threadIdx.x + k;
+      if (i < end && seg[i]) last = i;
+    }
+    if (last >= 0) atomicMax(s_last, last);
+    __syncthreads();
+    const int l = *s_last;
+    __syncthreads();
+    if (l >= 0) return zeros + (uint32_t)(end - 1 - l);
+    zeros += (uint32_t)win;
+    end = start;
+  }
+  return zeros;
+}
+
+// ORs a byte into global memory (bytes shared by two parts of a segment; pre-zeroed by k_huff_layout)
+__device__ __forceinline__ void atomic_or_byte(uint8_t *p, uint32_t v) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  atomicOr(reinterpret_cast<uint32_t *>(a & ~(uintptr_t)3), (v & 0xffu) << (8 * (a & 3)));
+}
+
+// grid (nseg * nsub, n), block kTokThreads.  seghist: [n][nseg * nsub][261].
 __global__ void __launch_bounds__(kTokThreads)
     k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist) {
   __shared__ uint32_t sh[kSyms];
   __shared__ uint32_t ws[kTokWarps + 1];
   __shared__ uint32_t rows[kTokThreads * kRowWords];
   __shared__ unsigned short ipos[kTokPiece];
+  __shared__ int s_last;
   for (int i = threadIdx.x; i < kSyms; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  const uint8_t *seg = in + (size_t)blockIdx.y * hg.in_stride + (size_t)blockIdx.x * hg.seg_size;
-  uint32_t carry = 0;
-  for (int base = 0; base < hg.seg_size; base += kTokPiece) {
+  const int b = blockIdx.x / hg.nsub, part = blockIdx.x - b * hg.nsub;
+  const uint8_t *seg0 = in + (size_t)blockIdx.y * hg.in_stride + (size_t)b * hg.seg_size;
+  const int p0 = part * hg.sub_size, plen = min(hg.sub_size, hg.seg_size - p0);
+  const uint8_t *seg = seg0 + p0;
+  uint32_t carry = part ? zeros_before(seg0, p0, &s_last) : 0u;
+  for (int base = 0; base < plen; base += kTokPiece) {
     PieceItems P;
-    carry = build_items(seg, hg.seg_size, base, rows, ipos, ws, carry, &P);
+    carry = build_items(seg, plen, base, rows, ipos, ws, carry, &P);
     for (int k = threadIdx.x; k < P.count; k += kTokThreads) {
       uint32_t z = item_gap(ipos, k, P.zeros_in), ex;
       while (z >= (uint32_t)kMaxRun) {
@@ -282,7 +323,7 @@ __global__ void __launch_bounds__(kTokThreads)
     }
     __syncthreads();  // rows / ipos are rewritten by the next piece
   }
-  if (threadIdx.x == 0 && carry) {  // the run still open at the segment end
+  if (threadIdx.x == 0 && carry && part == hg.nsub - 1) {  // the run still open at the segment end
     uint32_t z = carry, ex;
     while (z >= (uint32_t)kMaxRun) {
       atomicAdd(&sh[260], 1u);
@@ -291,7 +332,7 @@ __global__ void __launch_bounds__(kTokThreads)
     if (z) atomicAdd(&sh[run_symbol(z, &ex)], 1u);
   }
   __syncthreads();
-  uint32_t *dst = seghist + ((size_t)blockIdx.y * hg.nseg + blockIdx.x) * kSyms;
+  uint32_t *dst = seghist + ((size_t)blockIdx.y * hg.nseg * hg.nsub + blockIdx.x) * kSyms;
   for (int i = threadIdx.x; i < kSyms; i += blockDim.x) dst[i] = sh[i];
 }
 
@@ -451,6 +492,8 @@ struct LayoutChunk {
   const TreeOut *trees;     // [n]
   uint32_t *seg_bits;       // [n][nseg] out
   uint32_t *seg_pos;        // [n][nseg] out: absolute offset of the segment PAYLOAD inside the item
+  uint32_t *part_start;     // [n][nseg][nsub] out: first bit of every part inside its segment
+  int nsub;
   const uint8_t *prefix;    // bytes emitted before the chunk (container headers), may be null
   int prefix_len;
   int size_patch;           // offset inside the prefix of the u32 chunk size, or -1
@@ -494,11 +537,16 @@ __global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_con
     __syncthreads();
     unsigned long long mine = 0;
     for (int b = wid; b < C.nseg; b += kLayoutThreads / 32) {
-      const uint32_t *h = C.seghist + ((size_t)item * C.nseg + b) * kSyms;
       unsigned long long bits = 0;
-      for (int s = lane; s < kSyms; s += 32) bits += (unsigned long long)h[s] * s_lenx[s];
+      for (int part = 0; part < C.nsub; ++part) {
+        const uint32_t *h = C.seghist + (((size_t)item * C.nseg + b) * C.nsub + part) * kSyms;
+        unsigned long long pb = 0;
+        for (int s = lane; s < kSyms; s += 32) pb += (unsigned long long)h[s] * s_lenx[s];
 #pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+        for (int d = 16; d >= 1; d >>= 1) pb += __shfl_xor_sync(0xffffffffu, pb, d);
+        if (lane == 0) C.part_start[((size_t)item * C.nseg + b) * C.nsub + part] = (uint32_t)bits;
+        bits += pb;
+      }
       if (lane == 0) {
         C.seg_bits[(size_t)item * C.nseg + b] = (uint32_t)bits;
         const unsigned long long sz = (bits + 7) >> 3;
@@ -557,6 +605,11 @@ __global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_con
           h[3] = (uint8_t)(hi >> 8);
         }
         C.seg_pos[(size_t)item * C.nseg + b] = pos + run + ex + hdr;
+        // a byte shared by two parts is written with atomicOr from both sides: clear it
+        for (int part = 1; part < C.nsub; ++part) {
+          const uint32_t st = C.part_start[((size_t)item * C.nseg + b) * C.nsub + part];
+          if (st & 7) out[pos + run + ex + hdr + (st >> 3)] = 0;
+        }
       }
       run += tot;
     }
@@ -738,15 +791,17 @@ __device__ __forceinline__ void put64(uint32_t *win, uint32_t pos, uint64_t val,
 __global__ void __launch_bounds__(kTokThreads)
     k_huff_pack3(const uint8_t *__restrict__ in, HuffGeom hg, const TreeOut *__restrict__ trees,
                  const uint32_t *__restrict__ seg_bits, const uint32_t *__restrict__ seg_pos,
-                 const uint32_t *__restrict__ sizes, uint8_t *__restrict__ out, unsigned long long out_stride,
-                 int *err) {
+                 const uint32_t *__restrict__ part_start, const uint32_t *__restrict__ sizes,
+                 uint8_t *__restrict__ out, unsigned long long out_stride, int *err) {
   __shared__ uint32_t win[kWin2Words + 4];
   __shared__ uint2 s_tab[kSyms];
+  __shared__ int s_last;
   __shared__ uint32_t ws[kTokWarps + 1];
   __shared__ uint32_t s_half;
   __shared__ uint32_t rows[kTokThreads * kRowWords];
   __shared__ __align__(16) unsigned short ipos[kTokPiece + 8];
-  const int item = blockIdx.y, b = blockIdx.x, t = threadIdx.x;
+  const int item = blockIdx.y, t = threadIdx.x;
+  const int b = blockIdx.x / hg.nsub, part = blockIdx.x - b * hg.nsub;
   if (sizes[item] == 0) return;  // did not fit (k_huff_layout)
   const TreeOut *tr = trees + item;
   for (int s = t; s < kSyms; s += blockDim.x) {
@@ -755,21 +810,32 @@ __global__ void __launch_bounds__(kTokThreads)
   }
   for (int i = t; i < kWin2Words + 4; i += blockDim.x) win[i] = 0;
   __syncthreads();
-  const uint8_t *seg = in + (size_t)item * hg.in_stride + (size_t)b * hg.seg_size;
-  uint8_t *dst = out + (size_t)item * out_stride + seg_pos[(size_t)item * hg.nseg + b];
+  const uint8_t *seg0 = in + (size_t)item * hg.in_stride + (size_t)b * hg.seg_size;
+  const int p0 = part * hg.sub_size, plen = min(hg.sub_size, hg.seg_size - p0);
+  const uint8_t *seg = seg0 + p0;
+  // this part's bits start at bit `first_bit` of the segment and end where the next part starts
+  const size_t pidx = ((size_t)item * hg.nseg + b) * hg.nsub + part;
+  const uint32_t first_bit = part_start[pidx];
+  const uint32_t end_bit = part + 1 < hg.nsub ? part_start[pidx + 1] : seg_bits[(size_t)item * hg.nseg + b];
+  uint8_t *dst = out + (size_t)item * out_stride + seg_pos[(size_t)item * hg.nseg + b] + (first_bit >> 3);
+  bool first_shared = (first_bit & 7) != 0;  // byte 0 of dst also holds the last bits of the previous part
   const uint32_t full_bits = s_tab[260].y >> 8;  // one maximal run token
   const uint64_t full_tok = (uint64_t)s_tab[260].x | ((uint64_t)(kMaxRun - 279) << (s_tab[260].y & 255u));
 
-  uint32_t carry = 0;  // zeros of the run that is still open
-  uint32_t gbyte = 0;  // complete bytes already written to dst
-  uint32_t wfill = 0;  // bits in the window; window bit 0 = bit 0 of byte gbyte
+  uint32_t carry = part ? zeros_before(seg0, p0, &s_last) : 0u;  // zeros of the run that is still open
+  uint32_t gbyte = 0;                                            // complete bytes already written to dst
+  uint32_t wfill = first_bit & 7;  // bits in the window; window bit 0 = bit 0 of byte gbyte
   // Writes the complete bytes of the window to dst and keeps the unfinished byte.  Uniform call.
   auto flush = [&]() {
     __syncthreads();
     const uint32_t nbytes = wfill >> 3;
     const uint8_t *wb = reinterpret_cast<const uint8_t *>(win);
     uint8_t *o = dst + gbyte;
-    for (uint32_t i = t; i < nbytes; i += kTokThreads) o[i] = wb[i];
+    for (uint32_t i = t; i < nbytes; i += kTokThreads) {
+      if (i == 0 && first_shared) atomic_or_byte(o, wb[0]);
+      else o[i] = wb[i];
+    }
+    if (nbytes) first_shared = false;
     const uint32_t keep = (wfill & 7) ? wb[nbytes] : 0u;
     __syncthreads();
     const uint32_t used = min((wfill >> 5) + 4u, (uint32_t)(kWin2Words + 4));
@@ -794,9 +860,9 @@ __global__ void __launch_bounds__(kTokThreads)
     }
   };
 
-  for (int base = 0; base < hg.seg_size; base += kTokPiece) {
+  for (int base = 0; base < plen; base += kTokPiece) {
     PieceItems P;
-    carry = build_items(seg, hg.seg_size, base, rows, ipos, ws, carry, &P);
+    carry = build_items(seg, plen, base, rows, ipos, ws, carry, &P);
     // a first gap of 16662 zeros or more: its maximal tokens go out first, the remainder stays with item 0
     uint32_t gap0_cut = 0;
     if (P.count > 0) {
@@ -896,8 +962,8 @@ __global__ void __launch_bounds__(kTokThreads)
     }
     __syncthreads();  // rows / ipos are rewritten by the next piece
   }
-  // the run still open at the segment end
-  if (carry) {
+  // the run still open at the segment end (an open run at the end of a part belongs to the next part)
+  if (carry && part == hg.nsub - 1) {
     emit_full_runs(carry / kMaxRun);
     const uint32_t rest = carry % kMaxRun;
     if (rest) {
@@ -912,9 +978,12 @@ __global__ void __launch_bounds__(kTokThreads)
   flush();
   // final partial byte (its padding bits are zero here; k_huff_stale adds the stale ones)
   if (t == 0) {
-    const uint32_t gbits = gbyte * 8u + wfill;
-    if (wfill) dst[gbyte] = (uint8_t)win[0];
-    if (gbits != seg_bits[(size_t)item * hg.nseg + b]) atomicMax(err, 99);  // internal consistency
+    const uint32_t gbits = (first_bit & ~7u) + gbyte * 8u + wfill;
+    if (wfill) {
+      if (part + 1 < hg.nsub || first_shared) atomic_or_byte(dst + gbyte, win[0]);
+      else dst[gbyte] = (uint8_t)win[0];
+    }
+    if (gbits != end_bit) atomicMax(err, 99);  // internal consistency
   }
 }
 
