@@ -657,6 +657,38 @@ int decode_team(long long streams, int out_bytes, int base) {
   return team;
 }
 
+// One unframed stream per item, decoded by a thread-block cluster of kDecCluster CTAs (distributed
+// shared memory) when there are few, large streams: a single image's low-res chunk.
+constexpr int kDecCluster = 8;
+bool use_decode_cluster(long long streams, int out_bytes) { return streams <= 16 && out_bytes >= (64 << 10); }
+int launch_stream_cluster(himgcu_ctx *ctx, const char *name, int n, const uint8_t *d_in, const ChunkDesc *d_cd,
+                          const DecTree *d_tree, const SegRef *d_seg, int out_seg, uint8_t *d_out,
+                          unsigned long long out_stride, int *d_status) {
+  // Not the widest team possible: where the stream is periodic (flat areas repeat one code) wrongly
+  // started decoders never re-synchronise and the rounds advance one subsequence at a time, so very
+  // short subsequences cost more rounds than they save work (measured on 4K and 8K images).
+  const int threads = out_seg >= (256 << 10) ? 512 : 256;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kDecCluster, n);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kDecCluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  {
+    LaunchScope ls_(ctx, name);
+    e = cudaLaunchKernelEx(&cfg, k_dec_stream_par<false, kDecCluster>, d_in, d_cd, d_tree, d_seg, 1, out_seg, d_out, out_stride,
+                           d_status);
+  }
+  if (e != cudaSuccess) return fail(ctx, HIMGCU_ERR_CUDA, "launch %s failed: %s", name, cudaGetErrorString(e));
+  return HIMGCU_OK;
+}
+
 // Whole-image decode of n streams resident on the device.
 int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long long *d_offsets,
                   const uint32_t *d_sizes, int n, const Geom &g, int flags, uint8_t *d_pixels, int *d_status) {
@@ -689,8 +721,14 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   // batch alone fills the GPU, wider teams when there are few streams (single images).
   const int lres_team = decode_team(n, g.lres_size, kParLresThreads);
   const int fres_team = decode_team((long long)n * g.rows, g.seg, kParFresThreads);
-  LAUNCH("k_dec_stream_lres", k_dec_stream_par<false>, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
-         g.lres_size, d_lres, g.lres_stride, d_status);
+  if (use_decode_cluster(n, g.lres_size) && !ctx->force_generic) {
+    int rc = launch_stream_cluster(ctx, "k_dec_stream_lres", n, d_himg, d_lcd, d_ltree, d_lseg, g.lres_size, d_lres,
+                                   (unsigned long long)g.lres_stride, d_status);
+    if (rc) return rc;
+  } else {
+    LAUNCH("k_dec_stream_lres", k_dec_stream_par<false>, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
+           g.lres_size, d_lres, g.lres_stride, d_status);
+  }
   if (fres_team == 32) {
     LAUNCH("k_dec_stream_fres", k_dec_stream_par<true>, dim3((g.rows + kParWarpTeams - 1) / kParWarpTeams, n),
            32 * kParWarpTeams, 0, d_himg, d_fcd, d_ftree, d_fseg, g.rows, g.seg, d_planes, g.planes_bytes, d_status);
@@ -1341,6 +1379,10 @@ int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_in, d_cd, d_tree, n, nseg, seg, whole ? 0 : 1, lenient, d_seg,
          d_status);
   const int team = decode_team((long long)n * nseg, seg, nseg == 1 ? kParLresThreads : kParFresThreads);
+  if (nseg == 1 && use_decode_cluster(n, seg) && !ctx->force_generic) {
+    return launch_stream_cluster(ctx, "k_dec_stream", n, d_in, d_cd, d_tree, d_seg, seg, d_out, (unsigned long long)out_stride,
+                                 d_status);
+  }
   if (team == 32) {
     LAUNCH("k_dec_stream", k_dec_stream_par<true>, dim3((nseg + kParWarpTeams - 1) / kParWarpTeams, n), 32 * kParWarpTeams, 0,
            d_in, d_cd, d_tree, d_seg, nseg, seg, d_out, (unsigned long long)out_stride, d_status);

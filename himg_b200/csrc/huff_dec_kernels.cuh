@@ -10,6 +10,8 @@
 #ifndef HIMG_B200_HUFF_DEC_KERNELS_CUH_
 #define HIMG_B200_HUFF_DEC_KERNELS_CUH_
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace himgcu {
@@ -484,7 +486,12 @@ constexpr int kParWarpTeams = 8;  // WARP_TEAMS: streams (one warp each) per CTA
 //   streams of the same image per CTA.  They share the image's LUT and tree in shared memory (1 KiB
 //   of shared memory per stream instead of 12 KiB, so the kernel leaves room for CTAs of other
 //   streams' kernels) and synchronise with __syncwarp only.
-template <bool WARP_TEAMS>
+// CL > 1 (with WARP_TEAMS = false): grid (nseg * CL, n) launched as thread-block CLUSTERS of CL CTAs:
+//   one team of CL * blockDim.x threads spread over CL SMs decodes one stream.  End positions,
+//   flags and scan totals are exchanged through distributed shared memory, team barriers are
+//   cluster barriers.  This is what a single large image needs: its low-res chunk is ONE stream,
+//   and one CTA (one SM) was the whole machine for it.
+template <bool WARP_TEAMS, int CL = 1>
 __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
                                  const DecTree *__restrict__ trees, const SegRef *__restrict__ segs, int nseg,
                                  int out_seg, uint8_t *__restrict__ out, unsigned long long out_stride,
@@ -494,13 +501,29 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   __shared__ uint32_t s_end_all[WARP_TEAMS ? 32 * kParWarpTeams : kParMaxTeam];
   __shared__ uint32_t ws[33];
   __shared__ int s_flags[3 * (WARP_TEAMS ? kParWarpTeams : 1)];
+  __shared__ uint32_t s_tot;
+  static_assert(!(WARP_TEAMS && CL > 1), "clusters are for the one-stream-per-team variant");
+  namespace cg = cooperative_groups;
   const int item = blockIdx.y;
+  const int rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int tm = WARP_TEAMS ? (int)(threadIdx.x >> 5) : 0;  // team inside the CTA
-  const int t = WARP_TEAMS ? (int)(threadIdx.x & 31) : (int)threadIdx.x, team = WARP_TEAMS ? 32 : (int)blockDim.x;
-  const int b = WARP_TEAMS ? (int)blockIdx.x * kParWarpTeams + tm : (int)blockIdx.x;
+  const int lt = WARP_TEAMS ? (int)(threadIdx.x & 31) : (int)threadIdx.x;  // index inside this CTA's share of the team
+  const int t = lt + rank * (int)blockDim.x, team = WARP_TEAMS ? 32 : CL * (int)blockDim.x;
+  const int b = WARP_TEAMS ? (int)blockIdx.x * kParWarpTeams + tm : (int)blockIdx.x / CL;
   auto tsync = [] {
     if (WARP_TEAMS) __syncwarp();
+    else if (CL > 1) cg::this_cluster().sync();
     else __syncthreads();
+  };
+  // OR of a per-CTA flag over the cluster (after a team barrier; ends with one, so the flag may be
+  // reused and a CTA may exit)
+  auto team_or = [&](int *flag) -> bool {
+    bool any = *flag != 0;
+    if (CL > 1) {
+      for (int r = 0; r < CL; ++r) any |= *cg::this_cluster().map_shared_rank(flag, r) != 0;
+      cg::this_cluster().sync();
+    }
+    return any;
   };
   const DecTree *T = trees + item;
   if (T->ok) {  // the whole CTA stages the image's LUT and tree
@@ -521,7 +544,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   int &s_changed = s_flags[3 * tm], &s_bad = s_flags[3 * tm + 1], &s_final = s_flags[3 * tm + 2];
   const uint32_t *SN = s_nodes;
   const uint32_t *lut = T->lut;
-  if (t == 0) s_bad = 0, s_final = -1;
+  if (lt == 0) s_bad = 0, s_final = -1;
+  int *final_pos = CL > 1 ? cg::this_cluster().map_shared_rank(&s_final, 0) : &s_final;  // lives in CTA 0
   tsync();
   const uint8_t *src = data + cd[item].off + sr.off;
   uint8_t *o = out + (size_t)item * out_stride + (size_t)b * out_seg;
@@ -647,12 +671,13 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
           if (i >= mi) cpp[i] = kPosInvalid;
       }
     }
-    s_end[t] = has_work ? endpos : kPosInvalid;
-    if (t == 0) s_changed = 0;
+    s_end[lt] = has_work ? endpos : kPosInvalid;
+    if (lt == 0) s_changed = 0;
     tsync();
     dirty = false;
     if (has_work && t > 0) {
-      const uint32_t prev = s_end[t - 1];
+      const uint32_t prev = (CL == 1 || lt > 0) ? s_end[lt - 1]
+                                                : cg::this_cluster().map_shared_rank(s_end, rank - 1)[blockDim.x - 1];
       // a start beyond my own range means the previous thread's token swallowed my subsequence
       if (prev != kPosInvalid && prev != start) {
         start = prev;
@@ -667,8 +692,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
       }
     }
     tsync();
-    if (!s_changed) break;
-    tsync();
+    if (!team_or(&s_changed)) break;
+    if (CL == 1) tsync();  // (team_or ends with a barrier when the team spans CTAs)
   }
 
   // ---- output offsets
@@ -685,11 +710,16 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   } else {
     uint32_t total;
     off = block_exscan_u32(has_work ? count : 0u, ws, &total);
+    if (CL > 1) {  // add the totals of the CTAs before mine
+      if (lt == 0) s_tot = total;
+      cg::this_cluster().sync();
+      for (int r = 0; r < rank; ++r) off += *cg::this_cluster().map_shared_rank(&s_tot, r);
+    }
   }
   // threads whose output lies inside the segment must have decoded cleanly
   if (has_work && off < (uint32_t)out_seg && endpos == kPosInvalid) s_bad = 1;
   tsync();
-  if (s_bad) {
+  if (team_or(&s_bad)) {
     if (t == 0) atomicMax(&status[item], 1);
     return;
   }
@@ -714,7 +744,7 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
           }
           br.consume(nb + nx);
           n += gb;
-          if (n == out_seg) s_final = (int)br.pos;
+          if (n == out_seg) *final_pos = (int)br.pos;
           continue;
         }
         if (!nb && (g.x & kLutLong)) long_node = (int)((g.x >> 4) & 0xffffu);
@@ -727,14 +757,15 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
       }
       if (lit) o[n] = (uint8_t)lit;
       n += z;
-      if (n == out_seg) s_final = (int)br.pos;
+      if (n == out_seg) *final_pos = (int)br.pos;
     }
     if (!ok) s_bad = 1;
   }
   tsync();
+  const bool any_bad = team_or(&s_bad);
   if (t == 0) {
     // complete output, and the read position inside the last byte (BitStream::AtTheEnd)
-    const bool ok = !s_bad && s_final >= 0 && (uint32_t)s_final > 8u * (sr.size - 1) && (uint32_t)s_final <= total_bits;
+    const bool ok = !any_bad && s_final >= 0 && (uint32_t)s_final > 8u * (sr.size - 1) && (uint32_t)s_final <= total_bits;
     if (!ok) atomicMax(&status[item], 1);
   }
 }
