@@ -543,6 +543,8 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   TreeOut *d_trees[2];
   uint32_t *d_seghist[2], *d_bits[2], *d_pos[2];
   uint32_t *d_part[2];
+  TreeParams TP;
+  memset(&TP, 0, sizeof(TP));
   for (int k = 0; k < nchunks; ++k) {
     HuffGeom &hg = chunks[k].hg;
     // Parts per segment: only worth it when the segments alone cannot fill the GPU (single images:
@@ -565,7 +567,9 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     dim3 grid(hg.nseg * hg.nsub, n);
     if (ctx->force_generic) LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
     else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
-    LAUNCH("k_huff_tree", k_huff_tree, n, kTreeThreads, 0, d_seghist[k], hg.nseg * hg.nsub, d_trees[k], d_err);
+    TP.seghist[k] = d_seghist[k];
+    TP.trees[k] = d_trees[k];
+    TP.rows[k] = hg.nseg * hg.nsub;
     LayoutChunk &C = P.ch[k];
     C.seghist = d_seghist[k];
     C.trees = d_trees[k];
@@ -580,6 +584,7 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     C.framed = hg.nseg > 1 ? 1 : 0;
     prefix_off += chunks[k].prefix.size();
   }
+  LAUNCH("k_huff_tree", k_huff_tree, dim3(n, nchunks), kTreeThreads, 0, TP, d_err);
   LAUNCH("k_huff_layout", k_huff_layout, n, kLayoutThreads, 0, P);
   const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);
   static bool attr_set = false;
@@ -711,8 +716,7 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   const unsigned nb = (unsigned)((n + 127) / 128);
   LAUNCH("k_dec_parse", k_dec_parse, nb, 128, 0, d_himg, d_offsets, d_sizes, n, g.w, g.h, g.nch, d_lcd, d_fcd,
          d_tabs, d_status);
-  LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_himg, d_lcd, lenient, d_ltree, d_status);
-  LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_himg, d_fcd, lenient, d_ftree, d_status);
+  LAUNCH("k_dec_tree", k_dec_tree, dim3(n, 2), kDecTreeThreads, 0, d_himg, d_lcd, d_fcd, lenient, d_ltree, d_ftree, d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_lcd, d_ltree, n, 1, g.lres_size, 0, lenient, d_lseg,
          d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
@@ -1375,7 +1379,7 @@ int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in
   ENSURE("stage_dseg", (size_t)n * nseg * sizeof(SegRef), d_seg);
   const unsigned nb = (unsigned)((n + 127) / 128);
   LAUNCH("k_dec_make_desc", k_dec_make_desc, nb, 128, 0, (unsigned long long)in_stride, d_in_sizes, n, d_cd, d_status);
-  LAUNCH("k_dec_tree", k_dec_tree, n, kDecTreeThreads, 0, d_in, d_cd, lenient, d_tree, d_status);
+  LAUNCH("k_dec_tree", k_dec_tree, dim3(n, 1), kDecTreeThreads, 0, d_in, d_cd, d_cd, lenient, d_tree, d_tree, d_status);
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_in, d_cd, d_tree, n, nseg, seg, whole ? 0 : 1, lenient, d_seg,
          d_status);
   const int team = decode_team((long long)n * nseg, seg, nseg == 1 ? kParLresThreads : kParFresThreads);

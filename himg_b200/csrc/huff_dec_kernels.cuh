@@ -179,10 +179,13 @@ __global__ void k_dec_make_desc(unsigned long long stride, const uint32_t *__res
 // ---- tree recovery (huffman_dec.cpp:152-213) ---------------------------------------------------
 constexpr int kDecTreeThreads = 256;
 
-// grid (n).
+// grid (n, 1 or 2): blockIdx.y selects the chunk (cd0 / trees0 or cd1 / trees1), so that the two
+// trees of an image are recovered side by side.
 __global__ void __launch_bounds__(kDecTreeThreads)
-    k_dec_tree(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd, int lenient,
-               DecTree *__restrict__ trees, int *__restrict__ status) {
+    k_dec_tree(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd0, const ChunkDesc *__restrict__ cd1,
+               int lenient, DecTree *__restrict__ trees0, DecTree *__restrict__ trees1, int *__restrict__ status) {
+  const ChunkDesc *__restrict__ cd = blockIdx.y ? cd1 : cd0;
+  DecTree *__restrict__ trees = blockIdx.y ? trees1 : trees0;
   __shared__ uint8_t raw[kTreeBytesMax + 8];
   __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
   __shared__ uint8_t depth[kMaxNodes];

@@ -339,9 +339,17 @@ __global__ void __launch_bounds__(kTokThreads)
 // ---- K-tree ----------------------------------------------------------------------------------
 constexpr int kTreeThreads = 288;
 
-// grid (n).  err: set to HIMGCU_ERR_UNSUPPORTED (5) if a code exceeds 32 bits.
+// The (up to two) chunks of an image get their trees in ONE launch: the construction is a serial
+// chain of ~80 us per tree, and two CTAs run it side by side.
+struct TreeParams {
+  const uint32_t *seghist[2];  // [n][rows][261]
+  TreeOut *trees[2];           // [n]
+  int rows[2];                 // histogram rows per item (segments x parts)
+};
+
+// grid (n, chunks).  err: set to HIMGCU_ERR_UNSUPPORTED (5) if a code exceeds 32 bits.
 __global__ void __launch_bounds__(kTreeThreads)
-    k_huff_tree(const uint32_t *__restrict__ seghist, int nseg, TreeOut *__restrict__ trees, int *err) {
+    k_huff_tree(const TreeParams P, int *err) {
   __shared__ uint32_t cnt[kMaxNodes];
   __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
   __shared__ short lq[kSyms];
@@ -357,12 +365,24 @@ __global__ void __launch_bounds__(kTreeThreads)
   __shared__ uint32_t st_code[kSyms + 1];
 
   const int t = threadIdx.x;
-  TreeOut *out = trees + blockIdx.x;
+  const uint32_t *__restrict__ seghist = P.seghist[blockIdx.y];
+  const int nseg = P.rows[blockIdx.y];
+  TreeOut *out = P.trees[blockIdx.y] + blockIdx.x;
   // 1. chunk histogram = sum of its segments' histograms (coalesced across threads)
   uint32_t my = 0;
   if (t < kSyms) {
+    // independent loads, eight in flight: one dependent L2 round trip per segment made this loop the
+    // longest part of the kernel for tall images
     const uint32_t *p = seghist + (size_t)blockIdx.x * nseg * kSyms + t;
-    for (int s = 0; s < nseg; ++s) my += p[(size_t)s * kSyms];
+    int s = 0;
+    for (; s + 8 <= nseg; s += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (size_t)(s + k) * kSyms);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) my += v[k];
+    }
+    for (; s < nseg; ++s) my += __ldg(p + (size_t)s * kSyms);
     out->hist[t] = my;
     s_code[t] = 0;
     s_len[t] = 0;
