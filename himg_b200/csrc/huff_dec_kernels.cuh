@@ -30,6 +30,10 @@ constexpr int kLutSize = 1 << kLutBits;
 //   bit 30     invalid slot (incomplete tree or symbol > 260)
 //   bit 31     code longer than kLutBits: bits 0-15 hold the tree node reached after kLutBits bits
 constexpr uint32_t kLutLong = 0x80000000u, kLutInvalid = 0x40000000u;
+// Second level for codes longer than the window: every internal node at depth kLutBits gets a table
+// of the next kSubBits bits (entries as above with the length counted from the window's end; a
+// code longer than kLutBits + kSubBits keeps kLutLong | node and is finished by a tree walk).
+constexpr int kSubBits = 5, kSubCap = 64;
 
 __host__ __device__ inline uint32_t lut_entry(int sym, int len) {
   if (sym > 260) return kLutInvalid;
@@ -58,13 +62,15 @@ struct ChunkDesc {
 //      the first non-zero literal
 //   y: bits 0-7 first non-zero literal, 8-17 offset of the second, 18-25 its value, 26-27 number of
 //      non-zero literals
-// No token (x bits 0-3 = 0): x = kLutLong | node << 4 (the first code is longer than the window; node
-// reached after kLutBits bits), kLutInvalid, or 0 (single-leaf tree).
+// No token (x bits 0-3 = 0): x = kLutLong | node << 4 | (second-level table + 1) << 14 (the first code
+// is longer than the window; node reached after kLutBits bits), kLutInvalid, or 0 (single-leaf tree).
 struct __align__(16) DecTree {
   uint32_t lut[kLutSize];  // see lut_entry()
   uint2 lut2[kLutSize];
   uint32_t nodes[kMaxNodes + 1];  // leaf: 0x80000000 | symbol; internal: child0 | child1 << 16 (0xffff = none)
+  uint32_t sub[kSubCap << kSubBits];
   int nnodes;
+  int nsub;      // second-level tables in use
   int data_off;  // first byte after the (byte-aligned) tree
   int ok;
   int single;    // single-leaf tree
@@ -194,6 +200,10 @@ __global__ void __launch_bounds__(kDecTreeThreads)
   __shared__ int stk_slot[kMaxNodes + 2];
   __shared__ uint8_t stk_depth[kMaxNodes + 2];
   __shared__ unsigned short stk_code[kMaxNodes + 2];
+  __shared__ short anc[kMaxNodes], stk_anc[kMaxNodes + 2];      // ancestor at depth kLutBits (-1: none)
+  __shared__ uint8_t subc[kMaxNodes], stk_sub[kMaxNodes + 2];   // code bits kLutBits .. kLutBits + kSubBits - 1
+  __shared__ short xsub[kMaxNodes];                             // second-level table of a depth-kLutBits node
+  __shared__ int s_nsub;
   const int item = blockIdx.x, t = threadIdx.x;
   DecTree *out = trees + item;
   const ChunkDesc d = cd[item];
@@ -207,11 +217,16 @@ __global__ void __launch_bounds__(kDecTreeThreads)
     stk_slot[0] = -1;
     stk_depth[0] = 0;
     stk_code[0] = 0;
+    stk_anc[0] = -1;
+    stk_sub[0] = 0;
+    s_nsub = 0;
     sp = ok ? 1 : 0;
     while (sp && ok) {
       --sp;
       const int slot = stk_slot[sp], dep = stk_depth[sp];
       const unsigned short code = stk_code[sp];
+      const short my_anc = stk_anc[sp];
+      const uint8_t my_sub = stk_sub[sp];
       if (n >= kMaxNodes) {
         ok = 0;
         break;
@@ -221,6 +236,8 @@ __global__ void __launch_bounds__(kDecTreeThreads)
       nsym[k] = -1;
       depth[k] = (uint8_t)dep;
       pcode[k] = code;
+      anc[k] = my_anc;
+      subc[k] = my_sub;
       if (slot >= 0) {
         if (slot & 1) cb[slot >> 1] = (short)k;
         else ca[slot >> 1] = (short)k;
@@ -242,13 +259,20 @@ __global__ void __launch_bounds__(kDecTreeThreads)
       } else {
         const int nd = min(dep + 1, 255);
         const unsigned short cbit = dep < kLutBits ? (unsigned short)(code | (1u << dep)) : code;
+        const short canc = dep == kLutBits ? (short)k : my_anc;  // children of a depth-kLutBits node start a sub-code
+        const int sb = dep - kLutBits;                           // position of the child's bit inside the sub-code
+        const uint8_t sub1 = (sb >= 0 && sb < kSubBits) ? (uint8_t)(my_sub | (1u << sb)) : my_sub;
         stk_slot[sp] = k * 2 + 1;
         stk_depth[sp] = (uint8_t)nd;
         stk_code[sp] = cbit;
+        stk_anc[sp] = canc;
+        stk_sub[sp] = sub1;
         ++sp;
         stk_slot[sp] = k * 2;
         stk_depth[sp] = (uint8_t)nd;
         stk_code[sp] = code;
+        stk_anc[sp] = canc;
+        stk_sub[sp] = my_sub;
         ++sp;
       }
     }
@@ -262,6 +286,7 @@ __global__ void __launch_bounds__(kDecTreeThreads)
     if (t == 0) {
       out->ok = 0;
       out->nnodes = 0;
+      out->nsub = 0;
       out->data_off = 0;
       out->single = 0;
       atomicMax(&status[item], 1);
@@ -291,14 +316,42 @@ __global__ void __launch_bounds__(kDecTreeThreads)
     out->data_off = (s_bits + 7) >> 3;
     out->single = single ? 1 : 0;
   }
-  __syncthreads();  // out->lut is complete (written by this CTA)
+  // second-level tables of the internal nodes at depth kLutBits
+  for (int i = t; i < (kSubCap << kSubBits); i += blockDim.x) out->sub[i] = kLutInvalid;
+  for (int k = t; k < n; k += blockDim.x) {
+    xsub[k] = -1;
+    if (nsym[k] < 0 && depth[k] == kLutBits) {
+      const int si = atomicAdd(&s_nsub, 1);
+      if (si < kSubCap) xsub[k] = (short)si;
+    }
+  }
+  __syncthreads();
+  for (int k = t; k < n; k += blockDim.x) {
+    const int d = (int)depth[k] - kLutBits;
+    if (d < 1 || d > kSubBits || anc[k] < 0 || xsub[anc[k]] < 0) continue;
+    uint32_t *tab = out->sub + ((int)xsub[anc[k]] << kSubBits);
+    if (nsym[k] >= 0) {
+      const uint32_t e = lut_entry(nsym[k], d);
+      for (uint32_t i = 0; i < (1u << (kSubBits - d)); ++i) tab[(i << d) | subc[k]] = e;
+    } else if (d == kSubBits) {
+      tab[subc[k]] = kLutLong | (uint32_t)k;
+    }
+  }
+  if (t == 0) out->nsub = min(s_nsub, kSubCap);
+  __syncthreads();  // out->lut and out->sub are complete (written by this CTA)
   for (int p = t; p < kLutSize; p += blockDim.x) {
     int pos = 0, bytes = 0, nlit = 0, tail = 0;
     uint32_t off[2] = {0, 0}, lit[2] = {0, 0}, first = 0;
     while (!single && pos < kLutBits) {
       const uint32_t e = out->lut[(uint32_t)p >> pos];
       if (e & (kLutLong | kLutInvalid)) {
-        if (pos == 0) first = (e & kLutInvalid) ? kLutInvalid : (kLutLong | ((e & 0xffffu) << 4));
+        if (pos == 0) {
+          first = kLutInvalid;
+          if (!(e & kLutInvalid)) {
+            const int node = (int)(e & 0xffffu);
+            first = kLutLong | ((uint32_t)node << 4) | ((uint32_t)(xsub[node] + 1) << 14);
+          }
+        }
         break;
       }
       const int len = (int)((e >> 8) & 31u), nx = (int)((e >> 13) & 15u);
@@ -467,6 +520,19 @@ __device__ __forceinline__ int decode_long(PBits &b, const uint32_t *nodes, int 
   b.refill();
   return finish_token(b, e, lit);
 }
+// Same with the second-level table of the node (g = the multi-token LUT word of the window): one
+// more lookup resolves codes of up to kLutBits + kSubBits bits; longer ones walk the tree.
+__device__ __forceinline__ int decode_long2(PBits &b, const uint32_t *nodes, const uint32_t *sub, uint32_t g, int *lit) {
+  const uint32_t si = (g >> 14) & 0xffu;
+  if (si) {
+    const uint32_t e = sub[((si - 1u) << kSubBits) + ((uint32_t)(b.buf >> kLutBits) & ((1u << kSubBits) - 1u))];
+    if (!(e & (kLutLong | kLutInvalid))) {
+      b.consume(kLutBits);
+      return finish_token(b, e, lit);  // >= 33 bits were buffered: 11 + 5 + 14 fit
+    }
+  }
+  return decode_long(b, nodes, (int)((g >> 4) & 0x3ffu), lit);
+}
 __device__ __forceinline__ int decode_token(PBits &b, const uint32_t *lut, const uint32_t *nodes, int *lit) {
   b.refill();
   const uint32_t e = __ldg(lut + ((uint32_t)b.buf & (kLutSize - 1)));
@@ -501,10 +567,13 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
                                  int *__restrict__ status) {
   __shared__ __align__(16) uint2 lut2[kLutSize];  // the single-token LUT stays in global memory (rare path)
   __shared__ uint32_t s_nodes[kMaxNodes + 1];
+  __shared__ uint32_t s_sub[kSubCap << kSubBits];
   __shared__ uint32_t s_end_all[WARP_TEAMS ? 32 * kParWarpTeams : kParMaxTeam];
   __shared__ uint32_t ws[33];
   __shared__ int s_flags[3 * (WARP_TEAMS ? kParWarpTeams : 1)];
   __shared__ uint32_t s_tot;
+  // WARP_TEAMS: one 32-byte output line per lane (word w of lane l at [warp][w][l]: conflict-free)
+  __shared__ uint32_t s_line[WARP_TEAMS ? kParWarpTeams * 8 * 32 : 1];
   static_assert(!(WARP_TEAMS && CL > 1), "clusters are for the one-stream-per-team variant");
   namespace cg = cooperative_groups;
   const int item = blockIdx.y;
@@ -535,6 +604,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
     for (int i = threadIdx.x; i < kLutSize / 2; i += blockDim.x) reinterpret_cast<uint4 *>(lut2)[i] = __ldg(l2 + i);
     const int nn = T->nnodes;
     for (int i = threadIdx.x; i < nn; i += blockDim.x) s_nodes[i] = T->nodes[i];
+    const int ns = T->nsub << kSubBits;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) s_sub[i] = T->sub[i];
   }
   __syncthreads();
   if (WARP_TEAMS && b >= nseg) return;
@@ -556,8 +627,8 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
 
   // The segment is zero-filled cooperatively (coalesced stores); the write pass then only stores
   // the non-zero literals -- three out of four coefficient bytes are zeros at quality 50.
+  const bool al16 = ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)out_seg) & 15) == 0;
   {
-    const bool al16 = ((reinterpret_cast<uintptr_t>(o) | (uintptr_t)out_seg) & 15) == 0;
     if (al16) {
       for (int i = t; i < (out_seg >> 4); i += team) reinterpret_cast<uint4 *>(o)[i] = make_uint4(0, 0, 0, 0);
     } else {
@@ -637,8 +708,10 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
           next_ms = mi < kCp ? bound_lo + (64u << mi) : 0xffffffffu;
         }
         br.refill();
-        // every token of the window starts in my range, and even a 14-bit tail ends inside the stream
-        if (br.pos + kLutBits <= bound_hi && br.pos + kLutBits + 14 <= total_bits) {
+        // A group that STARTS in my range is mine even if its later tokens start beyond bound_hi: the
+        // next thread begins wherever I end.  Only the last bits of the stream (where the padding
+        // would be parsed as tokens) go through the single-token path.
+        if (br.pos + kLutBits + 14 <= total_bits) {
           const uint32_t g = lut2[(uint32_t)br.buf & (kLutSize - 1)].x;
           if (g & 15u) {
             const int nb = (int)(g & 15u), nx = (int)((g >> 14) & 15u);
@@ -648,7 +721,7 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
           }
           if (g & kLutLong) {  // code longer than the window: no second table lookup
             int lit;
-            const int z = decode_long(br, SN, (int)((g >> 4) & 0xffffu), &lit);
+            const int z = decode_long2(br, SN, s_sub, g, &lit);
             if (z < 0 || br.pos > total_bits) {
               ok = false;
               break;
@@ -728,40 +801,78 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   }
 
   // ---- phase 2: decode again and write the non-zero literals
+  // One byte store per literal makes one 32-byte L2 write transaction per literal: the kernel was bound
+  // by that, not by instructions.  A lane therefore collects the literals of the 32-byte lines that
+  // lie completely inside its own output range in a shared-memory line and writes each line once
+  // (two 16-byte stores, zeros included); only its first and last, shared, lines take byte stores.
   if (has_work && off < (uint32_t)out_seg && start < total_bits) {
     PBits br;
     br.seek(src, sr.size, start);
     int n = (int)off;
     bool ok = true;
+    uint32_t *line = s_line + (WARP_TEAMS ? tm * 256 + lt : 0);
+    const int line_lo = (WARP_TEAMS && al16) ? (int)((off + 31u) >> 5) : 0x7fffffff;
+    const int line_hi = (int)(min(off + count, (uint32_t)out_seg) >> 5);
+    int cur = -1;
+    if (WARP_TEAMS) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) line[k * 32] = 0;
+    }
+    auto flush_line = [&]() {
+      if (WARP_TEAMS && cur >= 0) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          w[k] = line[k * 32];
+          line[k * 32] = 0;
+        }
+        uint4 *d = reinterpret_cast<uint4 *>(o + (size_t)cur * 32);
+        d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    };
+    auto put = [&](int idx, uint32_t v) {
+      const int ln = idx >> 5;
+      if (WARP_TEAMS && ln >= line_lo && ln < line_hi) {
+        if (ln != cur) {
+          flush_line();
+          cur = ln;
+        }
+        reinterpret_cast<uint8_t *>(line + ((idx >> 2) & 7) * 32)[idx & 3] = (uint8_t)v;
+      } else {
+        o[idx] = (uint8_t)v;
+      }
+    };
     while (br.pos < bound_hi && n < out_seg) {
       br.refill();
-      int long_node = -1;
-      if (br.pos + kLutBits <= bound_hi && br.pos + kLutBits + 14 <= total_bits) {
+      uint32_t long_g = 0;
+      if (br.pos + kLutBits + 14 <= total_bits) {  // same rule as in phase 1
         const uint2 g = lut2[(uint32_t)br.buf & (kLutSize - 1)];
         const int nb = (int)(g.x & 15u), nx = (int)((g.x >> 14) & 15u);
         const int gb = (int)((g.x >> 4) & 1023u) + (int)((uint32_t)(br.buf >> nb) & ((1u << nx) - 1u));
         if (nb && n + gb <= out_seg) {  // the whole group lies inside the segment
           if (g.y >> 26) {
-            o[n + (int)((g.x >> 18) & 1023u)] = (uint8_t)g.y;
-            if ((g.y >> 26) > 1) o[n + (int)((g.y >> 8) & 1023u)] = (uint8_t)(g.y >> 18);
+            put(n + (int)((g.x >> 18) & 1023u), g.y);
+            if ((g.y >> 26) > 1) put(n + (int)((g.y >> 8) & 1023u), g.y >> 18);
           }
           br.consume(nb + nx);
           n += gb;
           if (n == out_seg) *final_pos = (int)br.pos;
           continue;
         }
-        if (!nb && (g.x & kLutLong)) long_node = (int)((g.x >> 4) & 0xffffu);
+        if (!nb && (g.x & kLutLong)) long_g = g.x;
       }
       int lit;
-      const int z = long_node >= 0 ? decode_long(br, SN, long_node, &lit) : decode_token(br, lut, SN, &lit);
+      const int z = long_g ? decode_long2(br, SN, s_sub, long_g, &lit) : decode_token(br, lut, SN, &lit);
       if (z < 0 || br.pos > total_bits || n + z > out_seg) {
         ok = false;  // a zero run that overshoots the segment is an error (huffman_dec.cpp:352)
         break;
       }
-      if (lit) o[n] = (uint8_t)lit;
+      if (lit) put(n, (uint32_t)lit);
       n += z;
       if (n == out_seg) *final_pos = (int)br.pos;
     }
+    flush_line();
     if (!ok) s_bad = 1;
   }
   tsync();

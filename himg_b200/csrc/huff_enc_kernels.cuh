@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(kHuffThreads)
 // gap_0 = p_0 + zeros carried in, gap_k = p_k - p_(k-1) - 1.  The run that is still open at the end
 // of a piece is carried to the next piece; at the segment end it is emitted by one thread.
 // =================================================================================================
-constexpr int kTokThreads = 256;
+#ifndef HIMG_TOK_THREADS
+#define HIMG_TOK_THREADS 256
+#endif
+constexpr int kTokThreads = HIMG_TOK_THREADS;
 constexpr int kTokPiece = kTokThreads * kChunkBytes;  // 8 KiB
 constexpr int kTokWarps = kTokThreads / 32;
 
