@@ -298,7 +298,7 @@ __device__ __forceinline__ void atomic_or_byte(uint8_t *p, uint32_t v) {
 }
 
 // grid (nseg * nsub, n), block kTokThreads.  seghist: [n][nseg * nsub][261].
-__global__ void __launch_bounds__(kTokThreads)
+__global__ void __launch_bounds__(kTokThreads, 8)
     k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist) {
   __shared__ uint32_t sh[kSyms];
   __shared__ uint32_t ws[kTokWarps + 1];
