@@ -185,6 +185,10 @@ __global__ void __launch_bounds__(kLresWarps * 32)
                 unsigned long long unmap_stride) {
   __shared__ uint8_t sL[kLresWarps * 2][16][16];
   __shared__ uint8_t sR[kLresWarps * 2][16][17];
+  // The codes of a macroblock are contiguous in memory but the wavefront touches them along
+  // diagonals: one byte per lane and step would be one 32-byte L2 transaction per byte.  They pass
+  // through shared memory and move in rows of consecutive bytes instead (as do the decoded samples).
+  __shared__ uint8_t sC[kLresWarps * 2][256];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
   const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
   const long long mb = ((long long)blockIdx.x * kLresWarps + wid) * 2 + half;
@@ -210,8 +214,8 @@ __global__ void __launch_bounds__(kLresWarps * 32)
   int p = 0;
   if (ENCODE) {
     // stage the macroblock (row hl) and pick the predictor
-    if (active && hl < bh)
-      for (int du = 0; du < bw; ++du) sL[slot][hl][du] = Lin[plane + (size_t)(16 * mv + hl) * g.cols + 16 * mu + du];
+    if (active && hl < bw)  // lane = column: every load instruction reads one row of consecutive bytes
+      for (int dv = 0; dv < bh; ++dv) sL[slot][dv][hl] = __ldg(Lin + plane + (size_t)(16 * mv + dv) * g.cols + 16 * mu + hl);
     __syncwarp();
     int err[5] = {0, 0, 0, 0, 0};
     if (active && hl < bh) {
@@ -249,7 +253,11 @@ __global__ void __launch_bounds__(kLresWarps * 32)
     if (active && hl == 0) *selp = (uint8_t)sel;
     p = sel + 2;  // DecodePredictor widens first: 254/255 -> 256/257 -> default formula
   } else {
-    if (active) p = (int)(*selp) + 2;
+    if (active) {
+      p = (int)(*selp) + 2;
+      for (int i = hl; i < bh * bw; i += 16) sC[slot][i] = dp[i];
+    }
+    __syncwarp();
   }
 
   // wavefront: lane hl owns column du = hl; at step s it handles row dv = s - du
@@ -274,15 +282,21 @@ __global__ void __launch_bounds__(kLresWarps * 32)
         const int d = (int)sL[slot][dv][du] - pr;
         const int m = __ldg(map_lut + (d < 0 ? -d : d));
         code = d >= 0 ? m : ((256 - m) & 0xff);
-        dp[dv * bw + du] = (uint8_t)code;
+        sC[slot][dv * bw + du] = (uint8_t)code;
       } else {
-        code = dp[dv * bw + du];
+        code = sC[slot][dv * bw + du];
       }
       const int rec = clamp255((int)(short)(pr + __ldg(un + code)));
       sR[slot][dv][du] = (uint8_t)rec;
-      if (!ENCODE) Rout[plane + (size_t)(16 * mv + dv) * g.cols + 16 * mu + du] = (uint8_t)rec;
     }
     __syncwarp();
+  }
+  if (active) {
+    if (ENCODE) {
+      for (int i = hl; i < bh * bw; i += 16) dp[i] = sC[slot][i];
+    } else if (hl < bw) {
+      for (int dv = 0; dv < bh; ++dv) Rout[plane + (size_t)(16 * mv + dv) * g.cols + 16 * mu + hl] = sR[slot][dv][hl];
+    }
   }
 }
 
