@@ -572,8 +572,9 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   __shared__ uint32_t ws[33];
   __shared__ int s_flags[3 * (WARP_TEAMS ? kParWarpTeams : 1)];
   __shared__ uint32_t s_tot;
-  // WARP_TEAMS: one 32-byte output line per lane (word w of lane l at [warp][w][l]: conflict-free)
-  __shared__ uint32_t s_line[WARP_TEAMS ? kParWarpTeams * 8 * 32 : 1];
+  // one 32-byte output line per lane (word w of lane l at [warp][w][l]: conflict-free); CTAs of more
+  // than eight warps (wide teams for a few large streams) write their literals directly
+  __shared__ uint32_t s_line[kParWarpTeams * 8 * 32];
   static_assert(!(WARP_TEAMS && CL > 1), "clusters are for the one-stream-per-team variant");
   namespace cg = cooperative_groups;
   const int item = blockIdx.y;
@@ -810,16 +811,17 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
     br.seek(src, sr.size, start);
     int n = (int)off;
     bool ok = true;
-    uint32_t *line = s_line + (WARP_TEAMS ? tm * 256 + lt : 0);
-    const int line_lo = (WARP_TEAMS && al16) ? (int)((off + 31u) >> 5) : 0x7fffffff;
+    const bool buffered = (reinterpret_cast<uintptr_t>(o) & 15) == 0 && blockDim.x <= 32 * kParWarpTeams;
+    uint32_t *line = s_line + (buffered ? (threadIdx.x >> 5) * 256 + (threadIdx.x & 31) : 0);
+    const int line_lo = buffered ? (int)((off + 31u) >> 5) : 0x7fffffff;
     const int line_hi = (int)(min(off + count, (uint32_t)out_seg) >> 5);
     int cur = -1;
-    if (WARP_TEAMS) {
+    if (buffered) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) line[k * 32] = 0;
     }
     auto flush_line = [&]() {
-      if (WARP_TEAMS && cur >= 0) {
+      if (cur >= 0) {
         uint32_t w[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -833,7 +835,7 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
     };
     auto put = [&](int idx, uint32_t v) {
       const int ln = idx >> 5;
-      if (WARP_TEAMS && ln >= line_lo && ln < line_hi) {
+      if (ln >= line_lo && ln < line_hi) {
         if (ln != cur) {
           flush_line();
           cur = ln;
