@@ -547,13 +547,13 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   memset(&TP, 0, sizeof(TP));
   for (int k = 0; k < nchunks; ++k) {
     HuffGeom &hg = chunks[k].hg;
-    // Parts per segment: only worth it when the segments alone cannot fill the GPU (single images:
-    // the whole low-res chunk is ONE unframed segment).  Target ~2 CTAs per SM, parts of >= 8 KiB.
+    // Parts per segment: only worth it when the segments alone cannot fill the GPU (the low-res chunk
+    // of an image is ONE unframed segment: one CTA per image otherwise).  Parts of >= 8 KiB.
     hg.nsub = 1;
     hg.sub_size = hg.seg_size;
-    const long long ctas = (long long)n * hg.nseg;
-    if (!ctx->force_generic && ctas < 296 && hg.seg_size > 2 * kTokPiece) {
-      const int want = (int)std::min<long long>(64, (296 + ctas - 1) / ctas);
+    const long long ctas = (long long)n * hg.nseg, fill = 148 * 8;  // CTAs that keep every SM busy
+    if (!ctx->force_generic && ctas < fill && hg.seg_size > 2 * kTokPiece) {
+      const int want = (int)std::min<long long>(64, (fill + ctas - 1) / ctas);
       const int sub = (int)((((long long)hg.seg_size + want - 1) / want + kTokPiece - 1) / kTokPiece) * kTokPiece;
       hg.sub_size = sub;
       hg.nsub = (hg.seg_size + sub - 1) / sub;
