@@ -551,7 +551,10 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     // of an image is ONE unframed segment: one CTA per image otherwise).  Parts of >= 8 KiB.
     hg.nsub = 1;
     hg.sub_size = hg.seg_size;
-    const long long ctas = (long long)n * hg.nseg, fill = 148 * 8;  // CTAs that keep every SM busy
+    // CTAs wanted: every SM busy for the one-CTA-per-image low-res chunk; framed chunks already have a
+    // CTA per block row and only get parts when even those are few (measured: more parts cost more
+    // in the layout and look-back steps than they gain)
+    const long long ctas = (long long)n * hg.nseg, fill = hg.nseg == 1 ? 148 * 8 : 148 * 2;
     if (!ctx->force_generic && ctas < fill && hg.seg_size > 2 * kTokPiece) {
       const int want = (int)std::min<long long>(64, (fill + ctas - 1) / ctas);
       const int sub = (int)((((long long)hg.seg_size + want - 1) / want + kTokPiece - 1) / kTokPiece) * kTokPiece;
