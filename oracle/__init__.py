@@ -303,7 +303,10 @@ class _Ref:
             raise RuntimeError("reference encode failed")
         return out[:n].tobytes()
 
-    def decode(self, data: bytes, max_threads=0):
+    def decode(self, data: bytes, max_threads=1):
+        """One worker thread by default: with max_threads=0 (hardware concurrency) the reference's
+        decoder crashes intermittently on images with fewer block rows than threads (observed on
+        520x24: 2 segfaults in 25 runs, none with one thread; decoder.cpp:274-329)."""
         buf = np.frombuffer(data, np.uint8)
         w, h, n = C.c_int(), C.c_int(), C.c_int()
         cap = 1 << 16
