@@ -1,4 +1,6 @@
-"""Encode leg and decode leg of the host-buffer calls: alone, then concurrently from two threads."""
+"""Encode leg and decode leg of the host-buffer calls: alone, then concurrently from two threads
+(two contexts, both PCIe directions busy).  usage: e2e_duplex_probe.py [chunks] [sub_batch_MB] [lanes];
+TRACE_ONLY=1 prints the device-side timeline of one concurrent run (HIMG_DEBUG_PIPE)."""
 import sys, time, threading
 sys.path.insert(0, ".")
 import numpy as np, torch
@@ -8,12 +10,7 @@ from himg_b200.synth import synth_images
 W, H, NCH, Q, B, CH = 1920, 1080, 3, 50, 128, int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda:0")
 import os
-PE, PD = (sys.argv[4], sys.argv[5]) if len(sys.argv) > 5 else ("0", "0")
-os.environ["HIMG_STREAM_PRIORITY"] = PE
-ctx_e = himg_b200.Context(0)
-ctx_e.set_option("host_lanes", 4); ctx_e.encode_batch_host(torch.zeros((64, 64, 64, 3), dtype=torch.uint8).pin_memory().numpy() if False else np.zeros((64, 64, 64, 3), np.uint8), 50, True)  # create the lanes now
-os.environ["HIMG_STREAM_PRIORITY"] = PD
-ctx_d = himg_b200.Context(0)
+ctx_e, ctx_d = himg_b200.Context(0), himg_b200.Context(0)
 SUB = int(sys.argv[2]) << 20 if len(sys.argv) > 2 else 64 << 20
 LANES = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 ctx_e.set_option("host_lanes", LANES); ctx_d.set_option("host_lanes", LANES)
@@ -51,4 +48,4 @@ enc(); dec()
 import os
 if os.environ.get("TRACE_ONLY"):
     os.environ["HIMG_DEBUG_PIPE"] = "1"; torch.cuda.synchronize(); both(); sys.exit(0)
-print(f"prio={PE}/{PD} lanes={LANES} sub={SUB>>20}MB chunks={CH}: enc {timeit(enc):.1f} ms  dec {timeit(dec):.1f} ms  both(threads) {timeit(both):.1f} ms")
+print(f"lanes={LANES} sub={SUB>>20}MB chunks={CH}: enc {timeit(enc):.1f} ms  dec {timeit(dec):.1f} ms  both(threads) {timeit(both):.1f} ms")
