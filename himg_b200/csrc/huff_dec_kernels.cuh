@@ -3,10 +3,11 @@
 // over-read (the reference's unchecked fast loop has undefined behaviour there).
 //
 //   k_dec_parse    one thread per image: RIFF/FRMT/LMAP/LRES/QCFG/FMAP/FRES walk + table recovery
-//   k_dec_tree     one CTA per chunk: serialised tree -> node arrays + single- and multi-token LUTs
-//   k_dec_segtab   one thread per chunk: walk the 2/4-byte segment headers
-//   k_dec_stream   one thread per segment: LUT decode + tree walk for long codes + zero-run
-//                  expansion, 32-bit stores (the format's segments are independently decodable)
+//   k_dec_tree        one CTA per chunk: serialised tree -> packed nodes, single- and multi-token LUTs,
+//                     second-level tables for codes longer than the LUT window
+//   k_dec_segtab      one thread per chunk: walk the 2/4-byte segment headers
+//   k_dec_stream_par  a team of threads per stream (warp per block-row segment / CTA / cluster of
+//                     CTAs): subsequence-parallel, self-synchronising decode (see the kernel)
 #ifndef HIMG_B200_HUFF_DEC_KERNELS_CUH_
 #define HIMG_B200_HUFF_DEC_KERNELS_CUH_
 

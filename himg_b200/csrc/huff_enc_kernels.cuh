@@ -1,12 +1,14 @@
 // RLE + Huffman ENCODE kernels (reference: huffman_enc.cpp:98-363).
 //
-//   k_huff_hist    block-parallel zero-run tokenisation + 261-bin histogram per segment
+//   k_huff_hist2   zero-run tokenisation over a balanced item list + 261-bin histogram per segment
+//                  (or per part of a segment)
 //   k_huff_tree    one CTA per chunk: histogram total -> Huffman tree with the reference's exact
 //                  tie-breaking -> (code,len) table + serialised tree
-//   k_huff_layout  per item: segment bit lengths (histogram . code length), prefix sum of
-//                  (header + payload) sizes -> absolute byte offsets; writes container headers
-//   k_huff_pack    CTA per segment: token bit lengths -> scan -> thread-local bit accumulation
-//                  into a shared-memory bit window -> bytes to the final position
+//   k_huff_layout  per item: segment bit lengths (histogram . code length), first bit of every part,
+//                  prefix sum of (header + payload) sizes -> absolute byte offsets; container headers
+//   k_huff_pack3   CTA per segment (or part): tokens built once in registers -> scan of bit totals ->
+//                  word-wise accumulation into a shared-memory bit window -> bytes to the final position
+//   k_huff_hist / k_huff_pack   first-generation kernels (per-thread chunk walks): the force_generic path
 //   k_huff_stale   the reference's uncleared scratch buffer leaks "stale" bits into the padding of
 //                  every segment's last byte; reproduced as a fix-up pass
 //

@@ -1,4 +1,5 @@
-// K-inv, fast path (v2).  Same arithmetic as k_inverse (xform_kernels.cuh): gather + dequantise +
+// K-inv, one block per thread in int32 with staged planes (v2): the path of 4-channel images; 1- and
+// 3-channel images take the lane-pair kernel of xform_inv3.cuh.  Same arithmetic as k_inverse (xform_kernels.cuh): gather + dequantise +
 // inverse WHT with floor >>3 after each pass + low-res add + clamp + inverse colour map
 // (decoder.cpp:366-423).  Differences are structural:
 //
@@ -8,8 +9,8 @@
 //  * 256-thread CTAs whose warps pass the per-channel phases in lock-step (instruction cache);
 //  * per-image dequantisation tables (they travel in-band) live in shared memory.
 //
-// The inverse cannot use the 16-bit lane-pair trick of K-fwd: the row pass sums eight int16 values
-// before its floor shift, which needs 19 bits.
+// (The row pass sums eight int16 values before its floor shift: 19 bits.  k_inverse3 packs two blocks
+// per register anyway, guarded by a range vote.)
 //
 // Preconditions (host checked, else k_inverse): width % 128 == 0 or cols % 16 == 0, height % 8 == 0,
 // 16-byte aligned planes / pixels, nch in {1,3,4}.
