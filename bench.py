@@ -288,26 +288,34 @@ def main():
 
     def e2e_pipelined(reps):
         ready, free = queue.SimpleQueue(), [threading.Semaphore(1), threading.Semaphore(1)]
+        stop = threading.Event()
 
         def encode_leg():
             try:
                 for k in range(reps):
                     b = k & 1
                     free[b].acquire()
+                    if stop.is_set():
+                        return
                     ctx_e.encode_batch_host(h_pixels, QUALITY, True, out=h_out2[b], offsets=h_off2[b], sizes=h_sizes2[b])
                     ready.put(b)
             except Exception as e:  # surface in the main thread
                 ready.put(e)
 
-        th = threading.Thread(target=encode_leg)
+        th = threading.Thread(target=encode_leg, daemon=True)
         th.start()
-        for _ in range(reps):
-            b = ready.get()
-            if isinstance(b, Exception):
-                raise b
-            ctx_d.decode_batch_host(h_out2[b], h_off2[b], h_sizes2[b], W, H, NCH, out=h_dec, status=h_status)
-            free[b].release()
-        th.join()
+        try:
+            for _ in range(reps):
+                b = ready.get(timeout=120)
+                if isinstance(b, Exception):
+                    raise b
+                ctx_d.decode_batch_host(h_out2[b], h_off2[b], h_sizes2[b], W, H, NCH, out=h_dec, status=h_status)
+                free[b].release()
+        finally:  # never leave the encode leg parked on a semaphore
+            stop.set()
+            for sem in free:
+                sem.release()
+            th.join(timeout=120)
 
     h_dec.zero_()
     e2e_pipelined(2)
