@@ -671,7 +671,7 @@ constexpr int kDecCluster = 8;
 bool use_decode_cluster(long long streams, int out_bytes) { return streams <= 16 && out_bytes >= (64 << 10); }
 int launch_stream_cluster(himgcu_ctx *ctx, const char *name, int n, const uint8_t *d_in, const ChunkDesc *d_cd,
                           const DecTree *d_tree, const SegRef *d_seg, int out_seg, uint8_t *d_out,
-                          unsigned long long out_stride, int *d_status) {
+                          unsigned long long out_stride, int *d_status, bool *launched) {
   // Not the widest team possible: where the stream is periodic (flat areas repeat one code) wrongly
   // started decoders never re-synchronise and the rounds advance one subsequence at a time, so very
   // short subsequences cost more rounds than they save work (measured on 4K and 8K images).
@@ -687,6 +687,14 @@ int launch_stream_cluster(himgcu_ctx *ctx, const char *name, int n, const uint8_
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  // a cluster of 8 CTAs must be co-schedulable (it is on a whole B200; not necessarily on a partitioned
+  // one): ask first, and let the caller fall back to the one-CTA team otherwise
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, k_dec_stream_par<false, kDecCluster>, &cfg) != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    *launched = false;
+    return HIMGCU_OK;
+  }
   cudaError_t e;
   {
     LaunchScope ls_(ctx, name);
@@ -694,6 +702,7 @@ int launch_stream_cluster(himgcu_ctx *ctx, const char *name, int n, const uint8_
                            d_status);
   }
   if (e != cudaSuccess) return fail(ctx, HIMGCU_ERR_CUDA, "launch %s failed: %s", name, cudaGetErrorString(e));
+  *launched = true;
   return HIMGCU_OK;
 }
 
@@ -728,11 +737,13 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   // batch alone fills the GPU, wider teams when there are few streams (single images).
   const int lres_team = decode_team(n, g.lres_size, kParLresThreads);
   const int fres_team = decode_team((long long)n * g.rows, g.seg, kParFresThreads);
+  bool clustered = false;
   if (use_decode_cluster(n, g.lres_size) && !ctx->force_generic) {
     int rc = launch_stream_cluster(ctx, "k_dec_stream_lres", n, d_himg, d_lcd, d_ltree, d_lseg, g.lres_size, d_lres,
-                                   (unsigned long long)g.lres_stride, d_status);
+                                   (unsigned long long)g.lres_stride, d_status, &clustered);
     if (rc) return rc;
-  } else {
+  }
+  if (!clustered) {
     LAUNCH("k_dec_stream_lres", k_dec_stream_par<false>, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
            g.lres_size, d_lres, g.lres_stride, d_status);
   }
@@ -1387,8 +1398,10 @@ int himgcu_stage_huff_uncompress(himgcu_ctx *ctx, const uint8_t *d_in, size_t in
          d_status);
   const int team = decode_team((long long)n * nseg, seg, nseg == 1 ? kParLresThreads : kParFresThreads);
   if (nseg == 1 && use_decode_cluster(n, seg) && !ctx->force_generic) {
-    return launch_stream_cluster(ctx, "k_dec_stream", n, d_in, d_cd, d_tree, d_seg, seg, d_out, (unsigned long long)out_stride,
-                                 d_status);
+    bool clustered = false;
+    int rc = launch_stream_cluster(ctx, "k_dec_stream", n, d_in, d_cd, d_tree, d_seg, seg, d_out, (unsigned long long)out_stride,
+                                   d_status, &clustered);
+    if (rc || clustered) return rc;
   }
   if (team == 32) {
     LAUNCH("k_dec_stream", k_dec_stream_par<true>, dim3((nseg + kParWarpTeams - 1) / kParWarpTeams, n), 32 * kParWarpTeams, 0,
