@@ -44,6 +44,8 @@ struct himgcu_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t in_stream = nullptr, out_stream = nullptr;  // copy streams of the host-buffer batch calls
+  cudaStream_t aux_stream = nullptr;                       // second branch of a single-image decode
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // The host-buffer batch calls keep up to kMaxLanes sub-batches in flight.  Lane 0 is this context;
   // lanes 1.. are child contexts (own stream, own workspace) so that the latency-bound kernels of one
   // sub-batch (tree construction, the low-res chunk) overlap the wide kernels of its neighbours.
@@ -729,24 +731,52 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   LAUNCH("k_dec_parse", k_dec_parse, nb, 128, 0, d_himg, d_offsets, d_sizes, n, g.w, g.h, g.nch, d_lcd, d_fcd,
          d_tabs, d_status);
   LAUNCH("k_dec_tree", k_dec_tree, dim3(n, 2), kDecTreeThreads, 0, d_himg, d_lcd, d_fcd, lenient, d_ltree, d_ftree, d_status);
-  LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_lcd, d_ltree, n, 1, g.lres_size, 0, lenient, d_lseg,
-         d_status);
+  // A single image is a chain of latency-bound kernels: its two branches (low-res stream -> DPCM, and
+  // segment table -> coefficient planes) share nothing until the inverse transform, so they run on
+  // two streams.  Batches fill the GPU on one stream (and device-side event waits are kept out of
+  // the multi-context host pipelines, see run_pipeline).
+  const bool fork = n == 1 && !ctx->profile;
+  cudaStream_t main_stream = ctx->stream;
+  if (fork) {
+    if (!ctx->aux_stream) {
+      CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ctx->ev_fork, main_stream));
+    CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    ctx->stream = ctx->aux_stream;  // the LAUNCH macro launches on ctx->stream
+  }
+  auto lres_branch = [&]() -> int {
+    LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_lcd, d_ltree, n, 1, g.lres_size, 0, lenient, d_lseg,
+           d_status);
+    // one CTA per stream.  Team size: 256 threads per LRES stream when the batch alone fills the GPU,
+    // wider teams (or a cluster of CTAs) when there are few streams (single images).
+    const int lres_team = decode_team(n, g.lres_size, kParLresThreads);
+    bool clustered = false;
+    if (use_decode_cluster(n, g.lres_size) && !ctx->force_generic) {
+      int rc = launch_stream_cluster(ctx, "k_dec_stream_lres", n, d_himg, d_lcd, d_ltree, d_lseg, g.lres_size, d_lres,
+                                     (unsigned long long)g.lres_stride, d_status, &clustered);
+      if (rc) return rc;
+    }
+    if (!clustered) {
+      LAUNCH("k_dec_stream_lres", k_dec_stream_par<false>, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
+             g.lres_size, d_lres, g.lres_stride, d_status);
+    }
+    const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
+    const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
+    LAUNCH("k_lres_dpcm_dec", (k_lres_dpcm<false>), blocks, kLresWarps * 32, 0, (const uint8_t *)nullptr, d_lres, d_R,
+           g, n, (const uint8_t *)nullptr, d_tabs->low_unmap, (unsigned long long)sizeof(DecTables));
+    return HIMGCU_OK;
+  };
+  int rc_l = lres_branch();
+  ctx->stream = main_stream;
+  if (rc_l) return rc_l;
+  if (fork) CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
          d_status);
-  // one CTA per stream.  Team size: a warp per block row / 256 threads per LRES stream when the
-  // batch alone fills the GPU, wider teams when there are few streams (single images).
-  const int lres_team = decode_team(n, g.lres_size, kParLresThreads);
+  // a warp per block row when the batch alone fills the GPU, wider teams for few streams
   const int fres_team = decode_team((long long)n * g.rows, g.seg, kParFresThreads);
-  bool clustered = false;
-  if (use_decode_cluster(n, g.lres_size) && !ctx->force_generic) {
-    int rc = launch_stream_cluster(ctx, "k_dec_stream_lres", n, d_himg, d_lcd, d_ltree, d_lseg, g.lres_size, d_lres,
-                                   (unsigned long long)g.lres_stride, d_status, &clustered);
-    if (rc) return rc;
-  }
-  if (!clustered) {
-    LAUNCH("k_dec_stream_lres", k_dec_stream_par<false>, dim3(1, n), lres_team, 0, d_himg, d_lcd, d_ltree, d_lseg, 1,
-           g.lres_size, d_lres, g.lres_stride, d_status);
-  }
   if (fres_team == 32) {
     LAUNCH("k_dec_stream_fres", k_dec_stream_par<true>, dim3((g.rows + kParWarpTeams - 1) / kParWarpTeams, n),
            32 * kParWarpTeams, 0, d_himg, d_fcd, d_ftree, d_fseg, g.rows, g.seg, d_planes, g.planes_bytes, d_status);
@@ -754,10 +784,7 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
     LAUNCH("k_dec_stream_fres", k_dec_stream_par<false>, dim3(g.rows, n), fres_team, 0, d_himg, d_fcd, d_ftree, d_fseg,
            g.rows, g.seg, d_planes, g.planes_bytes, d_status);
   }
-  const long long nmb = (long long)n * g.nch * g.mrows * g.mcols;
-  const unsigned blocks = (unsigned)((nmb + kLresWarps * 2 - 1) / (kLresWarps * 2));
-  LAUNCH("k_lres_dpcm_dec", (k_lres_dpcm<false>), blocks, kLresWarps * 32, 0, (const uint8_t *)nullptr, d_lres, d_R,
-         g, n, (const uint8_t *)nullptr, d_tabs->low_unmap, (unsigned long long)sizeof(DecTables));
+  if (fork) CK(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
   return stage_inverse(ctx, d_planes, d_R, n, g, d_tabs, sizeof(DecTables), d_pixels);
 }
 
@@ -994,6 +1021,9 @@ void himgcu_destroy(himgcu_ctx *ctx) {
     if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
   }
   // in_stream / out_stream are the process-wide copy queues: not destroyed here
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
