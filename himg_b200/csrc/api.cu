@@ -19,8 +19,10 @@
 #include "huff_enc_kernels.cuh"
 #include "tables.h"
 #include "xform_fwd2.cuh"
+#include "xform_fwd3.cuh"
 #include "xform_inv2.cuh"
 #include "xform_inv3.cuh"
+#include "xform_inv4.cuh"
 #include "xform_kernels.cuh"
 
 using namespace himgcu;
@@ -68,6 +70,7 @@ struct himgcu_ctx {
   size_t max_workspace = (size_t)24 << 30;
   size_t host_sub_bytes = (size_t)64 << 20;  // staged bytes per sub-batch of the host-buffer calls
   bool force_generic = false;  // tests: route everything through the generic kernels
+  int xform_variant = 0;       // experiments: 0 = newest fast kernels, 1 = previous generation
   // small table uploads are cached by key so that steady-state calls issue no host sync
   std::string qrec_key, lowres_key, prefix_key;  // device memory used per sub-batch of the host-buffer calls
 };
@@ -237,7 +240,7 @@ int upload_signed_lut(himgcu_ctx *ctx) {
 //   Cb = (b - g + 256) >> 1              = byte 1 of 128 * (b + (255 - g) + 1)     (g complemented by XOR)
 //   Cr = (r - g + 256) >> 1              = byte 1 of 128 * (r + (255 - g) + 1)
 //   plain channel                        = byte 0 of 1 * value
-void make_colour(int nch, bool ycbcr, Fwd2Params *P) {
+void make_colour(int nch, bool ycbcr, ColourW *cw) {
   for (int c = 0; c < 4; ++c) {
     uint32_t coef[4] = {0, 0, 0, 0}, add = 0, sel = 0x7430;
     bool xg = false;
@@ -250,7 +253,7 @@ void make_colour(int nch, bool ycbcr, Fwd2Params *P) {
     } else {
       coef[c] = 1;
     }
-    ColourW &w = P->cw[c];
+    ColourW &w = cw[c];
     w.add = add;
     w.sel = sel;
     w.has_xm = xg ? 1 : 0;
@@ -398,16 +401,61 @@ int launch_fwd2(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, in
   return HIMGCU_OK;
 }
 
+template <int NCH, int COLS>
+int launch_fwd3(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
+                const Fwd3Params &P, uint8_t *d_planes) {
+  const int total_pairs = g.rows * (g.cols / 2);
+  const int tiles = (total_pairs + kFwd3Threads - 1) / kFwd3Threads;
+  // consecutive tiles per CTA (the next tile loads under the tail of the current one): as many as
+  // leave at least four waves of CTAs on the GPU, at most 8
+  int tpc = (int)std::max<long long>(1, std::min<long long>(8, (long long)tiles * n / (148 * 2 * 4)));
+  if (ctx->xform_variant & 4) tpc = 1;  // experiment
+  dim3 grid((tiles + tpc - 1) / tpc, 1, n);
+  const int smem = ((2 * P.lut_half + 1 + 127) & ~127) + kFwd3Threads * 8 * 16 * NCH;
+  const uint8_t *lut = (const uint8_t *)ctx->signed_lut.p;
+  if (NCH >= 3 && ycbcr) {
+    constexpr bool Y = NCH >= 3;  // (no dead <1, true> instances)
+    CK(cudaFuncSetAttribute((k_forward3<NCH, Y, COLS>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LAUNCH("k_forward", (k_forward3<NCH, Y, COLS>), grid, kFwd3Threads, smem, d_pixels, d_L, g, P, lut, d_planes, tpc);
+  } else {
+    CK(cudaFuncSetAttribute((k_forward3<NCH, false, COLS>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    LAUNCH("k_forward", (k_forward3<NCH, false, COLS>), grid, kFwd3Threads, smem, d_pixels, d_L, g, P, lut, d_planes, tpc);
+  }
+  return HIMGCU_OK;
+}
+
 int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g,
                   const EncodeTables &t, uint8_t *d_planes) {
   // fast path: whole 16-pixel-wide block pairs, tightly packed pixels, 16-byte aligned rows
+  if (!ctx->force_generic && !(ctx->xform_variant & 1) && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_L) & 1) == 0 &&
+      (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
+    Fwd2Params P2;
+    if (make_quant_recs(t, &P2)) {
+      int rc = upload_signed_lut(ctx);
+      if (rc) return rc;
+      Fwd3Params P;
+      make_colour(g.nch, t.ycbcr, P.cw);
+      memcpy(P.rec, P2.rec, sizeof(P.rec));
+      P.lut_half = P2.lut_half;
+      // plane stride as an immediate for the common widths (1080p, 4K RGB; 8K gray)
+      if (g.nch == 3 && g.cols == 240) return launch_fwd3<3, 240>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+      if (g.nch == 3 && g.cols == 480) return launch_fwd3<3, 480>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+      if (g.nch == 1 && g.cols == 1024) return launch_fwd3<1, 1024>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
+      switch (g.nch) {
+        case 1: return launch_fwd3<1, 0>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
+        case 3: return launch_fwd3<3, 0>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+        default: return launch_fwd3<4, 0>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
+      }
+    }
+  }
   if (!ctx->force_generic && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
       (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
     Fwd2Params P;
     if (make_quant_recs(t, &P)) {
       int rc = upload_signed_lut(ctx);
       if (rc) return rc;
-      make_colour(g.nch, t.ycbcr, &P);
+      make_colour(g.nch, t.ycbcr, P.cw);
       // tile: up to 512 blocks per CTA; narrow images stack block rows so the CTA stays full
       P.tile_cols = std::min(g.cols, kFwd2Blocks);
       P.tile_rows = std::max(1, std::min(kFwd2Blocks / P.tile_cols, g.rows));
@@ -478,9 +526,32 @@ int launch_inv3_any(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R
   return launch_inv3<NCH, 64>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
 }
 
+template <int NCH>
+int launch_inv4(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
+                const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+  // per-image dequantisation tables first (the tables travel in-band); one set when the caller has one
+  const int ntab = tab_stride ? n : 1;
+  InvTables *d_inv;
+  ENSURE("inv_tables", (size_t)ntab * sizeof(InvTables), d_inv);
+  LAUNCH("k_inv_tables", k_inv_tables, ntab, 256, 0, d_tabs, tab_stride, d_inv);
+  const unsigned long long inv_stride = tab_stride ? sizeof(InvTables) : 0;
+  const int total_pairs = g.rows * (g.cols / 2);
+  dim3 grid((total_pairs + kInv4Threads - 1) / kInv4Threads, 1, n);
+  const int smem = NCH * 64 * 2 * kInv4Threads + 16 * 256 * 2 + 2 * 64 * 4;
+  CK(cudaFuncSetAttribute((k_inverse4<NCH>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  LAUNCH("k_inverse", (k_inverse4<NCH>), grid, kInv4Threads, smem, d_planes, d_R, g, d_inv, inv_stride, d_pixels);
+  return HIMGCU_OK;
+}
+
 int stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
                   const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
-  // lane-pair fast path: two blocks per thread, 16-byte pixel stores
+  // lane-pair fast path: two blocks per thread, flat tiles, 16-byte pixel stores
+  if (!ctx->force_generic && !(ctx->xform_variant & 1) && (g.h % 8) == 0 && (g.cols % 16) == 0 && (g.w % 16) == 0 &&
+      (g.nch == 1 || g.nch == 3) && (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_R) & 1) == 0) {
+    if (g.nch == 1) return launch_inv4<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    return launch_inv4<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+  }
   if (!ctx->force_generic && (g.h % 8) == 0 && (g.cols % 16) == 0 && (g.w % 16) == 0 && (g.nch == 1 || g.nch == 3) &&
       (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0) {
     if (g.nch == 1) return launch_inv3_any<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
@@ -999,6 +1070,7 @@ int himgcu_create(int device, himgcu_ctx **out) {
     return HIMGCU_ERR_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  if (const char *v = getenv("HIMG_XFORM_VARIANT")) ctx->xform_variant = atoi(v);  // experiments only
   *out = ctx;
   return HIMGCU_OK;
 }
@@ -1516,6 +1588,7 @@ uint64_t himgcu_launch_count(himgcu_ctx *ctx) { return ctx ? ctx->launches : 0; 
 int himgcu_set_option(himgcu_ctx *ctx, const char *name, long long value) {
   if (!ctx || !name) return HIMGCU_ERR_ARG;
   if (!strcmp(name, "force_generic")) ctx->force_generic = value != 0;
+  else if (!strcmp(name, "xform_variant")) ctx->xform_variant = (int)value;
   else if (!strcmp(name, "max_workspace_bytes")) ctx->max_workspace = (size_t)value;
   else if (!strcmp(name, "host_sub_batch_bytes")) ctx->host_sub_bytes = (size_t)std::max<long long>(value, 1 << 20);
   else if (!strcmp(name, "host_lanes")) ctx->host_lanes = (int)std::max<long long>(1, std::min<long long>(value, himgcu_ctx::kMaxLanes));

@@ -1,0 +1,358 @@
+// K-inv, fast path (v4): the roofline kernel of the decoder.
+//
+// Same arithmetic as k_inverse (xform_kernels.cuh): gather + dequantise + inverse WHT with a floor
+// >>3 after each pass + low-res add + clamp + inverse colour map (decoder.cpp:366-423,
+// quantize.cpp:153-165, hadamard.cpp:90-103, ycbcr.cpp:54-82).  The kernel is bound by the integer
+// (ALU) pipe, which accepts one warp instruction every other cycle, so the work is steered to the
+// FMA pipe (IMAD / IDP) wherever an instruction exists there:
+//
+//  * WARP TILES: a warp owns 32 consecutive block pairs of the image in row-major order (whatever the
+//    image width: no idle lanes on 1080p / 4K), stages their codes into its own shared-memory tile of
+//    [nch * 64 scan positions][32 pairs x 2 codes] with its own cp.async group, and never synchronises
+//    with the other warps of the CTA: while one warp waits for its codes the others compute, and the
+//    LSU-, FMA- and ALU-heavy phases of different warps overlap (see the kernel);
+//  * a thread owns two horizontally adjacent blocks as biased 16-bit lane pairs (exact while every
+//    dequantised coefficient lies in [-4096, 4095]; the warp votes and otherwise redoes the channel
+//    in int32 -- bit-exact either way, see v3);
+//  * dequantisation: the two codes of a lane pair arrive as ONE 16-bit load; each table address is
+//    ONE dp4a (byte * 2 + table base of the coefficient's shift: byte extraction, scaling and the
+//    add in a single FMA-pipe instruction); the table holds (int16)(unmap << s) + 4096;
+//  * the low-res corners are loaded by the owning thread while the tile is in flight;
+//  * low-res add + clamp is one DPX instruction per lane pair, so is every output of the inverse
+//    colour map; finished samples overwrite the thread's own codes in the tile.
+//
+// Preconditions (host checked, else k_inverse2 / k_inverse): cols % 16 == 0, height % 8 == 0,
+// 16-byte aligned planes / pixels, 2-byte aligned low-res image, nch in {1, 3}.
+#ifndef HIMG_B200_XFORM_INV4_CUH_
+#define HIMG_B200_XFORM_INV4_CUH_
+
+#include "common.cuh"
+#include "xform_fwd2.cuh"  // mid2 / nine2 / smem_u32
+#include "xform_inv2.cuh"  // cp_async16
+#include "xform_inv3.cuh"  // iwht8p
+
+namespace himgcu {
+
+constexpr int kInv4Threads = 256;  // 8 warps, each with its own tile of 32 block pairs
+
+// 8-point sequency-ordered WHT on lane pairs whose bias is B on entry, followed by a floor shift by
+// SH (0: none).  The bias on exit is 8 * B >> SH; no lane may leave 16 bits before the shift.
+template <uint32_t B, int SH>
+__device__ __forceinline__ void iwht8q(uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3, uint32_t &x4, uint32_t &x5,
+                                       uint32_t &x6, uint32_t &x7) {
+  constexpr uint32_t K1 = 2 * B * 0x00010001u, K2 = 4 * B * 0x00010001u, K3 = 8 * B * 0x00010001u;
+  constexpr uint32_t M = (0xffffu >> SH) * 0x00010001u;
+  uint32_t a0, a1, a2, a3, a4, a5, a6, a7, b0, b1, b2, b3, b4, b5, b6, b7;
+  ibfly<K1>(x0, x4, a0, a4);
+  ibfly<K1>(x1, x5, a1, a5);
+  ibfly<K1>(x2, x6, a2, a6);
+  ibfly<K1>(x3, x7, a3, a7);
+  ibfly<K2>(a0, a2, b0, b2);
+  ibfly<K2>(a1, a3, b1, b3);
+  ibfly<K2>(a4, a6, b4, b6);
+  ibfly<K2>(a5, a7, b5, b7);
+  ibfly<K3>(b0, b1, x0, x7);
+  ibfly<K3>(b4, b5, x1, x6);
+  ibfly<K3>(b6, b7, x2, x5);
+  ibfly<K3>(b2, b3, x3, x4);
+  if (SH) {
+    x0 = (x0 >> SH) & M;
+    x1 = (x1 >> SH) & M;
+    x2 = (x2 >> SH) & M;
+    x3 = (x3 >> SH) & M;
+    x4 = (x4 >> SH) & M;
+    x5 = (x5 >> SH) & M;
+    x6 = (x6 >> SH) & M;
+    x7 = (x7 >> SH) & M;
+  }
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// Dequantisation tables of one image, built once per image by k_inv_tables and copied into shared
+// memory by every CTA of K-inv (the tables travel in-band, so they differ from image to image).
+//   dq[s][code] = ((int16)(unmap[code] << s) >> pre) + bias       (quantize.cpp:153-165)
+// When every shift of the image is >= 3 (any quality up to ~60) all coefficients are multiples of 8 and
+// the row pass needs no floor at all: pre = 3, the tables hold value / 8 with a bias of 512 and the row
+// pass skips its shift + mask.  Otherwise pre = 0 and the bias is 4096.
+struct alignas(16) InvTables {
+  uint16_t dq[16][256];
+  uint32_t toff[2][64];  // byte offset of the table of coefficient j (class luma / chroma) inside dq
+  int pre, bias, ycbcr, pad;
+};
+
+// grid n, block 256.  (Shift bytes are masked: a rejected stream leaves its DecTables unspecified.)
+__global__ void k_inv_tables(const DecTables *__restrict__ tabs, unsigned long long tab_stride, InvTables *__restrict__ out) {
+  const DecTables *T = reinterpret_cast<const DecTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.x * tab_stride);
+  InvTables *O = out + blockIdx.x;
+  const int t = threadIdx.x;
+  const int mine = t < 128 ? (T->shift[t >> 6][t & 63] & 15) : 15;
+  const bool pre3 = __syncthreads_and(mine >= 3) != 0;
+  const int pre = pre3 ? 3 : 0, bias = pre3 ? 512 : 4096;
+  const int un = T->full_unmap[t];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) O->dq[s][t] = (uint16_t)(((int)(short)(un << s) >> pre) + bias);
+  if (t < 128) O->toff[t >> 6][t & 63] = (uint32_t)mine * 512u;
+  if (t == 0) {
+    O->pre = pre;
+    O->bias = bias;
+    O->ycbcr = T->ycbcr != 0 ? 1 : 0;
+    O->pad = 0;
+  }
+}
+
+// nine2 whose outputs are low-res - 4096 per lane (the addend of the fused add + clamp): the leaves of
+// the midpoint tree take the OR of 0xf000 in the same three-input logic operation as their mask.
+__device__ __forceinline__ void nine2m(uint32_t a, uint32_t b, uint32_t (&t)[9]) {
+  const uint32_t M = 0xf000f000u;
+  const uint32_t t4 = mid2(a, b), t2 = mid2(a, t4), t6 = mid2(t4, b);
+  t[0] = a | M;
+  t[2] = t2 | M;
+  t[4] = t4 | M;
+  t[6] = t6 | M;
+  t[1] = (((a + t2 + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
+  t[3] = (((t2 + t4 + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
+  t[5] = (((t4 + t6 + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
+  t[7] = (((t6 + b + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
+  t[8] = b | M;
+}
+
+// int32 redo of one channel of a thread's two blocks (some lane of the warp left [-4096, 4095]).
+// Reads the codes again; writes the clamped samples over them.
+__device__ __noinline__ void inv4_wide(uint8_t *cc, int pitch, const uint32_t *tab, uint32_t dq_base, uint32_t top, uint32_t bot,
+                                        int tab_bias, int pre) {
+#pragma unroll 1
+  for (int blk = 0; blk < 2; ++blk) {
+    int y32[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+      const uint32_t code = cc[scan_pos(j) * pitch + blk];
+      y32[j] = (int)(short)(lds_u16(dq_base + tab[j] + 2 * code) - tab_bias) << pre;  // exact: the low bits were zeros
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      wht8(y32[r * 8 + 0], y32[r * 8 + 1], y32[r * 8 + 2], y32[r * 8 + 3], y32[r * 8 + 4], y32[r * 8 + 5], y32[r * 8 + 6],
+           y32[r * 8 + 7]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y32[r * 8 + i] >>= 3;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      wht8(y32[q], y32[8 + q], y32[16 + q], y32[24 + q], y32[32 + q], y32[40 + q], y32[48 + q], y32[56 + q]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y32[i * 8 + q] >>= 3;
+    }
+    int lf[9], rt[9];
+    nine((int)((top >> (8 * blk)) & 0xffu), (int)((bot >> (8 * blk)) & 0xffu), lf);
+    nine((int)((top >> (8 * blk + 8)) & 0xffu), (int)((bot >> (8 * blk + 8)) & 0xffu), rt);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      int tl[9];
+      nine(lf[y], rt[y], tl);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        cc[(y * 8 + i) * pitch + blk] = (uint8_t)__vimin_s32_relu((int)(short)(y32[y * 8 + i] + tl[i]), 255);
+    }
+  }
+}
+
+// grid (ceil(rows * cols / 2 / 256), 1, n), block 256: one tile of 256 consecutive block pairs per CTA.
+// dynamic smem: tile [NCH * 64][512] | dq tables [16][256] u16 | table addresses [2][64] u32
+//
+// The codes of the tile and the image's tables arrive by cp.async (one warp per tile row: 512 contiguous
+// bytes per instruction), the CTA meets at one barrier, then the warps run the three channels and the
+// output phase WITHOUT further barriers: a thread only ever touches its own two byte columns of the tile,
+// and the phases of the inverse load different pipes (LSU in the gather, FMA in the butterflies, ALU in
+// the clamps), so warps that drift apart fill each other's gaps.
+// (Measured and dropped: several tiles per CTA with the next tile prefetched into L2 or copied early from
+// inside the output phase, and tiles owned by single warps -- all slower than fresh CTAs whose start-up
+// overlaps the other resident CTA.)
+template <int NCH>
+__global__ void __launch_bounds__(kInv4Threads, 2)
+    k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
+               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels) {
+  extern __shared__ __align__(128) uint8_t sPl[];
+  constexpr int TP = kInv4Threads, PITCH = 2 * TP;  // pairs per tile, bytes per tile row
+  uint8_t *sDq = sPl + NCH * 64 * PITCH;
+  uint32_t *sTab = reinterpret_cast<uint32_t *>(sDq + 16 * 256 * 2);
+
+  const int t = threadIdx.x;
+  const int PR = g.cols >> 1, total = g.rows * PR;
+  const int f0 = blockIdx.x * TP;
+  const int nact = min(TP, total - f0);
+  const uint8_t *ipl = planes + (size_t)blockIdx.z * g.planes_bytes;
+  uint8_t *img = pixels + (size_t)blockIdx.z * g.out_img_bytes;
+  const InvTables *T = reinterpret_cast<const InvTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tab_stride);
+  // block row / first pair of the tile's first element: one division per CTA, everything else by
+  // carrying (a tile spans few block rows unless the image is very narrow)
+  const int v0 = f0 / PR, p0 = f0 - v0 * PR;
+  auto locate = [&](int k, int &v, int &p) {  // element f0 + k of the image -> block row, pair in the row
+    if (PR >= 32) {
+      v = v0;
+      p = p0 + k;
+      while (p >= PR) {
+        p -= PR;
+        ++v;
+      }
+    } else {
+      v = (f0 + k) / PR;
+      p = f0 + k - v * PR;
+    }
+  };
+  {
+    // the image's tables (8704 bytes), then the tile: one warp per tile row, one 16-byte chunk (8 pairs of
+    // ONE block row: cols % 16 == 0) per lane
+    const uint4 *tsrc = reinterpret_cast<const uint4 *>(T);
+    for (int i = t; i < (16 * 256 * 2 + 2 * 64 * 4) / 16; i += kInv4Threads) cp_async16(sDq + 16 * i, tsrc + i);
+    const int lane = t & 31, w = t >> 5;
+    if (8 * lane < nact) {
+      int vl, pl;
+      locate(8 * lane, vl, pl);
+      const uint8_t *src = ipl + (size_t)vl * g.seg + 2 * pl + (size_t)w * g.cols;
+      uint8_t *dst = sPl + w * PITCH + lane * 16;
+      const size_t rstep = (size_t)8 * g.cols;
+#pragma unroll 8
+      for (int i = 0; i < NCH * 8; ++i) {
+        cp_async16(dst + i * 8 * PITCH, src);
+        src += rstep;
+      }
+    }
+  }
+  const int pre = T->pre, tab_bias = T->bias;
+  const bool pre3 = pre == 3;
+  const uint32_t wide_mask = pre3 ? 0xfc00fc00u : 0xe000e000u;  // a lane outside the table's narrow range
+  const bool ycbcr = T->ycbcr != 0;
+  const bool active = t < nact;
+  int v, p;
+  locate(active ? t : 0, v, p);
+  const int u = 2 * p;
+  // low-res corners (u, u+1, u+2) x (v, v+1), edge clamped; u and cols are even
+  uint32_t top[NCH], bot[NCH];
+  {
+    const int v2 = min(v + 1, g.rows - 1), u2 = min(u + 2, g.cols - 1);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const uint8_t *Rc = R + ((size_t)blockIdx.z * NCH + c) * g.rows * g.cols;
+      const uint8_t *r0 = Rc + (size_t)v * g.cols, *r1 = Rc + (size_t)v2 * g.cols;
+      top[c] = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(r0 + u)) | ((uint32_t)__ldg(r0 + u2) << 16);
+      bot[c] = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(r1 + u)) | ((uint32_t)__ldg(r1 + u2) << 16);
+    }
+  }
+  uint8_t *col = sPl + 2 * t;  // this thread's two byte columns of the tile
+  const uint32_t dq_base = smem_u32(sDq);  // (table offsets -> shared-memory addresses: added at the lookups' base)
+  cp_async_wait_all();
+  __syncthreads();  // the only barrier: from here on a thread touches its own two byte columns only
+#pragma unroll 1
+  for (int c = 0; c < NCH; ++c) {
+    uint8_t *cc = col + c * 64 * PITCH;
+    const uint32_t *tab = sTab + ((ycbcr && NCH >= 3 && (c == 1 || c == 2)) ? 64 : 0);
+    uint32_t tp = top[0], bt = bot[0];
+#pragma unroll
+    for (int k = 1; k < NCH; ++k) {
+      tp = c == k ? top[k] : tp;
+      bt = c == k ? bot[k] : bt;
+    }
+    // ---- gather + dequantise both blocks (biased lanes), remember every bit that was ever set
+    uint32_t x[64], seen = 0;
+#pragma unroll
+    for (int j4 = 0; j4 < 64; j4 += 4) {
+      const uint4 tb = *reinterpret_cast<const uint4 *>(tab + j4);
+      const uint32_t tbj[4] = {tb.x + dq_base, tb.y + dq_base, tb.z + dq_base, tb.w + dq_base};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = j4 + k;
+        const uint32_t w = *reinterpret_cast<const uint16_t *>(cc + scan_pos(j) * PITCH);
+        const uint32_t a = lds_u16(__dp4a(w, 0x00000002u, tbj[k]));  // table + 2 * code of block A
+        const uint32_t b = lds_u16(__dp4a(w, 0x00000200u, tbj[k]));  // table + 2 * code of block B
+        x[j] = a + (b << 16);
+      }
+      seen |= (x[j4] | x[j4 + 1]) | (x[j4 + 2] | x[j4 + 3]);  // (two three-input ORs)
+    }
+    const bool narrow = __all_sync(0xffffffffu, !active || (seen & wide_mask) == 0);
+    if (narrow) {
+      if (pre3) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          iwht8q<512, 0>(x[r * 8 + 0], x[r * 8 + 1], x[r * 8 + 2], x[r * 8 + 3], x[r * 8 + 4], x[r * 8 + 5], x[r * 8 + 6], x[r * 8 + 7]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          iwht8q<4096, 3>(x[r * 8 + 0], x[r * 8 + 1], x[r * 8 + 2], x[r * 8 + 3], x[r * 8 + 4], x[r * 8 + 5], x[r * 8 + 6], x[r * 8 + 7]);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        iwht8q<4096, 3>(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
+      uint32_t lf[9], rt[9];
+      nine2(__byte_perm(tp, 0u, 0x4140), __byte_perm(bt, 0u, 0x4140), lf);  // left columns: corners u | u+1
+      nine2(__byte_perm(tp, 0u, 0x4241), __byte_perm(bt, 0u, 0x4241), rt);  // right columns: u+1 | u+2
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        uint32_t tl[9];
+        nine2m(lf[y], rt[y], tl);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // lane + (low-res - 4096), min 255, max 0: two samples per instruction
+          const uint32_t px = __viaddmin_s16x2_relu(x[y * 8 + i], tl[i], 0x00ff00ffu);
+          // (inactive threads own their two columns of the tile too: no guard needed)
+          *reinterpret_cast<uint16_t *>(cc + (y * 8 + i) * PITCH) = (uint16_t)__byte_perm(px, 0u, 0x4420);
+        }
+      }
+    } else {
+      inv4_wide(cc, PITCH, tab, dq_base, tp, bt, tab_bias, pre);
+    }
+  }
+
+  // ---- inverse colour map + interleave + 16-byte stores (a thread reads back its own two columns)
+  {
+    const bool do_colour = ycbcr && NCH >= 3;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      uint32_t s[8 * NCH];  // lane pairs in memory order: pixel-major, channel-minor
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t ch[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          ch[c] = __byte_perm((uint32_t) * reinterpret_cast<const uint16_t *>(col + (c * 64 + y * 8 + i) * PITCH), 0u, 0x4140);
+        if (NCH >= 3 && do_colour) {
+          // cb = 2Cb - 255, cr = 2Cr - 255, G = Y - ((cb + cr + 2) >> 2) = Y + 128 - ((Cb + Cr + 2) >> 1)
+          const uint32_t h = ((ch[1] + ch[NCH >= 3 ? 2 : 0] + 0x00020002u) >> 1) & 0x01ff01ffu;
+          const uint32_t G = ch[0] + 0x01800180u - h;                      // G + 256 per lane, positive
+          const uint32_t cr = (ch[NCH >= 3 ? 2 : 0] << 1) + 0xfe01fe01u;   // cr - 256 per lane (int16)
+          const uint32_t cb = (ch[1] << 1) + 0xfe01fe01u;
+          ch[0] = __viaddmin_s16x2_relu(G, cr, 0x00ff00ffu);
+          ch[1] = __viaddmin_s16x2_relu(G, 0xff00ff00u, 0x00ff00ffu);
+          ch[NCH >= 3 ? 2 : 0] = __viaddmin_s16x2_relu(G, cb, 0x00ff00ffu);
+        }
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) s[i * NCH + c] = ch[c];
+      }
+      // words of block A and of block B: four consecutive lane pairs -> one word each
+      uint32_t wa[2 * NCH], wb[2 * NCH];
+#pragma unroll
+      for (int m = 0; m < 2 * NCH; ++m) {
+        const uint32_t pq = __byte_perm(s[4 * m], s[4 * m + 1], 0x6240), q = __byte_perm(s[4 * m + 2], s[4 * m + 3], 0x6240);
+        wa[m] = __byte_perm(pq, q, 0x5410);
+        wb[m] = __byte_perm(pq, q, 0x7632);
+      }
+      if (active) {
+        uint4 *dst = reinterpret_cast<uint4 *>(img + ((size_t)(8 * v + y) * g.w + (size_t)u * 8) * NCH);
+        if (NCH == 1) {
+          dst[0] = make_uint4(wa[0], wa[1], wb[0], wb[1]);
+        } else {
+          dst[0] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+          dst[1] = make_uint4(wa[4], wa[5], wb[0], wb[1]);
+          dst[2] = make_uint4(wb[2], wb[3], wb[4], wb[5]);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace himgcu
+
+#endif  // HIMG_B200_XFORM_INV4_CUH_

@@ -112,6 +112,28 @@ def test_stage_forward(ctx, port, shape, quality, ycbcr):
     assert_same(got, want, f"planes {shape} q{quality} ycbcr={yc}")
 
 
+# Flat tiles (256 consecutive block pairs per CTA, whatever the width): tiles that start and end inside
+# a block row, many block rows per tile (more than the 32 lanes that issue the bulk copies), rows wider
+# than a tile, a last tile with idle threads.
+FLAT_SHAPES = [(1920, 64, 3), (272, 200, 3), (16, 4104, 1), (4112, 16, 3), (3840, 24, 3), (1040, 72, 1), (304, 136, 4),
+               (32, 2072, 3)]
+
+
+@pytest.mark.parametrize("shape", FLAT_SHAPES)
+@pytest.mark.parametrize("quality,ycbcr", [(50, True), (100, True), (33, False)])
+def test_stage_forward_flat_tiles(ctx, port, shape, quality, ycbcr):
+    w, h, n = shape
+    img = port.synth(w, h, n, 17, 25)
+    yc = ycbcr and n >= 3
+    cm = port.rgb_to_ycbcr(img) if yc else img
+    L = port.lowres_sample(cm)
+    want = port.fullres_planes(cm, L, quality, yc)
+    got = ctx.stage_forward(dev(np.stack([img, img[::-1].copy()])), dev(np.stack([L, L])), quality, yc).cpu().numpy()
+    assert_same(got[0], want, f"planes {shape} q{quality} ycbcr={yc}")
+    cm1 = port.rgb_to_ycbcr(img[::-1].copy()) if yc else img[::-1].copy()
+    assert_same(got[1], port.fullres_planes(cm1, L, quality, yc), f"second image {shape}")
+
+
 def test_stage_forward_extreme_values(ctx, port):
     """Checkerboards drive |T| to its 16320 maximum and exercise the top of MapTo8Bit."""
     yy, xx = np.mgrid[0:64, 0:128]
@@ -315,7 +337,7 @@ def test_stage_inverse_random_planes(ctx, port, shape):
 
 
 @pytest.mark.parametrize("shape", [(128, 16, 3), (256, 24, 1), (640, 48, 3), (2176, 16, 3), (1920, 24, 3), (1024, 40, 1),
-                                   (4224, 8, 3)])
+                                   (4224, 8, 3), (1920, 64, 3), (384, 200, 1), (128, 2056, 3), (3840, 24, 3)])
 @pytest.mark.parametrize("kind", ["small", "mixed", "wild"])
 def test_stage_inverse_lane_pair_path(ctx, port, shape, kind):
     """Shapes that take the two-blocks-per-thread kernel (cols % 16 == 0): one, two and ragged tile
