@@ -14,11 +14,17 @@ import numpy as np
 from . import _native
 from ._native import HimgError, LENIENT, STRICT  # noqa: F401
 
-__all__ = ["Context", "Encoder", "Decoder", "HimgError", "STRICT", "LENIENT", "encode_bound"]
+__all__ = ["Context", "Encoder", "Decoder", "HimgError", "STRICT", "LENIENT", "encode_bound", "fnv1a64"]
 
 
 def encode_bound(w: int, h: int, nch: int) -> int:
     return int(_native.load().himgcu_encode_bound(w, h, nch))
+
+
+def fnv1a64(data) -> int:
+    """FNV-1a 64 of a bytes object / contiguous uint8 numpy array (SURVEY.md Appendix B checksum)."""
+    buf = np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, np.uint8)
+    return int(_native.load().himgcu_fnv1a64(buf.ctypes.data, buf.size))
 
 
 def _ptr(x):
@@ -41,6 +47,8 @@ class Context:
             raise HimgError(rc, f"cannot create a context on CUDA device {device} (no CPU fallback)")
         self.h = h
         self.device = device
+        self._explicit_stream = False  # set_stream() was called by the user
+        self._bound = None             # handle of the torch stream the tensor calls were last bound to
         if stream is not None:
             self.set_stream(stream)
 
@@ -63,11 +71,38 @@ class Context:
     def set_stream(self, stream):
         """stream: raw cudaStream_t handle (int; 0 = CUDA's legacy default stream) or a
         torch.cuda.Stream; None goes back to the context's own non-blocking stream."""
+        self._bound = None
         if stream is None:
+            self._explicit_stream = False
             self._check(self.lib.himgcu_reset_stream(self.h))
             return
+        self._explicit_stream = True
         handle = getattr(stream, "cuda_stream", stream)
         self._check(self.lib.himgcu_set_stream(self.h, C.c_void_p(int(handle))))
+
+    def _bind(self, *tensors, rows_ok=False):
+        """Called by every method that takes or returns torch tensors.  Checks that they are contiguous
+        uint8 / integer tensors on this context's device and -- unless the user chose a stream with
+        set_stream() -- runs the call on torch's CURRENT stream of that device, the stream the tensors were
+        produced on and will be consumed on (the context's own stream is not ordered against it)."""
+        import torch
+
+        for x in tensors:
+            if x is None:
+                continue
+            if not x.is_cuda or (x.device.index or 0) != self.device:
+                raise ValueError(f"tensor on {x.device}, the context is on cuda:{self.device}")
+            if not (x.is_contiguous() or (rows_ok and x.dim() >= 2 and x[0].is_contiguous())):
+                raise ValueError("tensors must be contiguous")
+        if not self._explicit_stream:
+            handle = torch.cuda.current_stream(self.device).cuda_stream
+            if handle != self._bound:
+                self._check(self.lib.himgcu_set_stream(self.h, C.c_void_p(int(handle))))
+                self._bound = handle
+
+    def encode_status(self):
+        """Synchronises and raises if an image of an earlier encode_batch could not be encoded."""
+        self._check(self.lib.himgcu_encode_status(self.h))
 
     def synchronize(self):
         self._check(self.lib.himgcu_synchronize(self.h))
@@ -104,6 +139,9 @@ class Context:
 
         n, h, w, nch = pixels.shape
         stride = (encode_bound(w, h, nch) + 255) & ~255
+        if pixels.dtype != torch.uint8:
+            raise ValueError("pixels must be uint8")
+        self._bind(pixels, out, sizes)
         if out is None:
             out = torch.empty((n, stride), dtype=torch.uint8, device=pixels.device)
         if sizes is None:
@@ -117,6 +155,7 @@ class Context:
         import torch
 
         n = offsets.numel()
+        self._bind(himg, offsets, sizes, out, status)
         if out is None:
             out = torch.empty((n, h, w, nch), dtype=torch.uint8, device=himg.device)
         if status is None:
@@ -155,6 +194,7 @@ class Context:
         import torch
 
         n, h, w, ps = pixels.shape
+        self._bind(pixels)
         nch = nch or ps
         rows, cols = (h + 7) >> 3, (w + 7) >> 3
         L = torch.empty((n, nch, rows, cols), dtype=torch.uint8, device=pixels.device)
@@ -165,6 +205,7 @@ class Context:
         import torch
 
         n, nch = L.shape[0], L.shape[1]
+        self._bind(L)
         stride = int(self.lib.himgcu_lres_stride(w, h, nch))
         size = int(self.lib.himgcu_lres_size(w, h, nch))
         out = torch.zeros((n, stride), dtype=torch.uint8, device=L.device)
@@ -175,6 +216,7 @@ class Context:
         import torch
 
         n, h, w, ps = pixels.shape
+        self._bind(pixels, L)
         nch = nch or ps
         rows, cols = (h + 7) >> 3, (w + 7) >> 3
         planes = torch.empty((n, rows * cols * 64 * nch), dtype=torch.uint8, device=pixels.device)
@@ -187,6 +229,7 @@ class Context:
         import torch
 
         n, in_size = data.shape
+        self._bind(data, rows_ok=True)  # (the row stride travels with the call)
         stride = (2 * in_size + 4096 + 255) & ~255
         out = torch.zeros((n, stride), dtype=torch.uint8, device=data.device)
         sizes = torch.zeros((n,), dtype=torch.int32, device=data.device)
@@ -198,6 +241,7 @@ class Context:
         import torch
 
         n = packed.shape[0]
+        self._bind(packed, sizes, rows_ok=True)
         stride = (out_size + 63) & ~63
         out = torch.zeros((n, stride), dtype=torch.uint8, device=packed.device)
         status = torch.zeros((n,), dtype=torch.int32, device=packed.device)
@@ -209,6 +253,7 @@ class Context:
         import torch
 
         n = lres.shape[0]
+        self._bind(lres, rows_ok=True)
         rows, cols = (h + 7) >> 3, (w + 7) >> 3
         un = np.ascontiguousarray(unmap, np.int16)
         R = torch.zeros((n, nch, rows, cols), dtype=torch.uint8, device=lres.device)
@@ -219,6 +264,7 @@ class Context:
         import torch
 
         n = planes.shape[0]
+        self._bind(planes, R)
         sl = np.ascontiguousarray(shift_luma, np.uint8)
         sc = np.ascontiguousarray(shift_chroma, np.uint8)
         un = np.ascontiguousarray(unmap, np.int16)

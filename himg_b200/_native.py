@@ -23,6 +23,7 @@ SIGNATURES = {
     "himgcu_reset_stream": (C.c_int, [C.c_void_p]),
     "himgcu_synchronize": (C.c_int, [C.c_void_p]),
     "himgcu_last_error": (C.c_char_p, [C.c_void_p]),
+    "himgcu_fnv1a64": (C.c_uint64, [_u8p, C.c_size_t]),
     "himgcu_encode_bound": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "himgcu_encode": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
                                 C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -31,6 +32,7 @@ SIGNATURES = {
                                 C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "himgcu_encode_batch": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _u8p,
                                       C.c_size_t, C.c_void_p]),
+    "himgcu_encode_status": (C.c_int, [C.c_void_p]),
     "himgcu_decode_batch": (C.c_int, [C.c_void_p, _u8p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, _u8p, C.c_void_p]),
     "himgcu_host_alloc": (C.c_void_p, [C.c_size_t]),

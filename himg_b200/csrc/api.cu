@@ -61,6 +61,8 @@ struct himgcu_ctx {
   DevBuf signed_lut;  // 32 KiB signed LUT (index m + 16384) for k_forward2
   void *pinned = nullptr;
   size_t pinned_cap = 0;
+  void *stage[2] = {nullptr, nullptr};  // page-locked staging slots of the single-image host calls
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   bool profile = false;
   std::vector<ProfRec> pending;
   std::vector<cudaEvent_t> event_pool;
@@ -72,7 +74,7 @@ struct himgcu_ctx {
   bool force_generic = false;  // tests: route everything through the generic kernels
   int xform_variant = 0;       // experiments: 0 = newest fast kernels, 1 = previous generation
   // small table uploads are cached by key so that steady-state calls issue no host sync
-  std::string qrec_key, lowres_key, prefix_key;  // device memory used per sub-batch of the host-buffer calls
+  std::string lowres_key, prefix_key;
 };
 
 namespace {
@@ -107,7 +109,6 @@ int ensure(himgcu_ctx *ctx, const char *name, size_t bytes, void **out) {
     const size_t want = (bytes + 255) & ~(size_t)255;
     CK(cudaMalloc(&b.p, want));
     b.cap = want;
-    ctx->qrec_key.clear();
     ctx->lowres_key.clear();
     ctx->prefix_key.clear();
   }
@@ -586,9 +587,13 @@ struct HuffChunkArgs {
 
 int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks, bool riff, uint8_t *d_out,
                       size_t out_stride, uint32_t *d_sizes) {
+  // Device error flag of the encoder (5: code longer than 32 bits, 4: output does not fit, 99: internal
+  // mismatch).  Sticky per context: cleared when it is read (take_enc_err), not per call, so that an
+  // error in an earlier sub-batch of an asynchronous call is not lost.
   int *d_err;
+  const bool fresh = ctx->bufs.find("enc_err") == ctx->bufs.end() || ctx->bufs["enc_err"].p == nullptr;
   ENSURE("enc_err", sizeof(int), d_err);
-  CK(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  if (fresh) CK(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
   LayoutParams P;
   memset(&P, 0, sizeof(P));
   P.nchunks = nchunks;
@@ -662,12 +667,7 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   }
   LAUNCH("k_huff_tree", k_huff_tree, dim3(n, nchunks), kTreeThreads, 0, TP, d_err);
   LAUNCH("k_huff_layout", k_huff_layout, n, kLayoutThreads, 0, P);
-  const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CK(cudaFuncSetAttribute(k_huff_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
-    attr_set = true;
-  }
+  const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);  // (below the 48 KiB that need no opt-in)
   for (int k = 0; k < nchunks; ++k) {
     const HuffGeom &hg = chunks[k].hg;
     dim3 grid(hg.nseg * hg.nsub, n);
@@ -690,7 +690,16 @@ int read_err_flag(himgcu_ctx *ctx, const char *name, int *value) {
   int *d_err;
   ENSURE(name, sizeof(int), d_err);
   CK(cudaMemcpyAsync(value, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));  // read = clear
   CK(cudaStreamSynchronize(ctx->stream));
+  return HIMGCU_OK;
+}
+
+// Status code of a device encoder error flag value (0 = none).
+int enc_err_status(himgcu_ctx *ctx, int err) {
+  if (err == 5) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "Huffman code longer than 32 bits");
+  if (err == 99) return fail(ctx, HIMGCU_ERR_CUDA, "internal: packed size mismatch");
+  if (err) return fail(ctx, HIMGCU_ERR_CAPACITY, "internal output bound exceeded");
   return HIMGCU_OK;
 }
 
@@ -842,8 +851,11 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   };
   int rc_l = lres_branch();
   ctx->stream = main_stream;
+  if (fork) {  // (also when the branch failed: its work must be ordered before the next call on the main stream)
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    if (rc_l) CK(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+  }
   if (rc_l) return rc_l;
-  if (fork) CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
   LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
          d_status);
   // a warp per block row when the batch alone fills the GPU, wider teams for few streams
@@ -995,7 +1007,7 @@ int finish_lanes(himgcu_ctx *ctx, int S) {
 // of one thread encoding and another decoding (both PCIe directions in use).
 // With pageable host memory the copies degrade to synchronous ones but stay correct.
 template <class FIn, class FRun, class FOut>
-int run_pipeline(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy_out) {
+int run_pipeline_steps(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy_out) {
   int n_in = 0, n_run = 0, n_out = 0;  // sub-batches copied in / launched / drained so far
   auto done = [&](cudaEvent_t e, bool *ok) -> int {
     const cudaError_t q = cudaEventQuery(e);
@@ -1044,6 +1056,24 @@ int run_pipeline(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy
   return finish_lanes(ctx, S);
 }
 
+// An error leaves sub-batches in flight (lanes still coding, copies queued on the shared streams that
+// write into the caller's buffers): drain everything before the caller sees the error and may free or
+// reuse its buffers.
+template <class FIn, class FRun, class FOut>
+int run_pipeline(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy_out) {
+  const int rc = run_pipeline_steps(ctx, K, S, copy_in, run, copy_out);
+  if (rc != HIMGCU_OK) {
+    const std::string why = ctx->err;
+    for (int b = 0; b < S; ++b) cudaStreamSynchronize(lane_of(ctx, b)->stream);
+    cudaStreamSynchronize(ctx->in_stream);
+    cudaStreamSynchronize(ctx->out_stream);
+    finish_lanes(ctx, S);
+    cudaGetLastError();
+    ctx->err = why;
+  }
+  return rc;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -1085,6 +1115,10 @@ void himgcu_destroy(himgcu_ctx *ctx) {
   if (ctx->full_lut.p) cudaFree(ctx->full_lut.p);
   if (ctx->signed_lut.p) cudaFree(ctx->signed_lut.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int k = 0; k < 2; ++k) {
+    if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
+    if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+  }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   for (himgcu_ctx *l : ctx->lanes) himgcu_destroy(l);
   for (int b = 0; b < himgcu_ctx::kMaxLanes; ++b) {
@@ -1102,8 +1136,9 @@ void himgcu_destroy(himgcu_ctx *ctx) {
 
 int himgcu_set_stream(himgcu_ctx *ctx, void *cuda_stream) {
   if (!ctx) return HIMGCU_ERR_ARG;
+  if (ctx->stream == reinterpret_cast<cudaStream_t>(cuda_stream)) return HIMGCU_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->stream);  // the context's scratch buffers are reused by the next call
   ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   return HIMGCU_OK;
 }
@@ -1126,14 +1161,22 @@ int himgcu_synchronize(himgcu_ctx *ctx) {
 
 const char *himgcu_last_error(himgcu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+uint64_t himgcu_fnv1a64(const uint8_t *data, size_t size) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i < size; ++i) h = (h ^ data[i]) * 0x100000001b3ull;
+  return h;
+}
+
 size_t himgcu_encode_bound(int w, int h, int nch) {
   if (!shape_ok(w, h, nch)) return 0;
   const Geom g = make_geom(w, h, nch, nch);
-  // RIFF(12) FRMT(19) LMAP(136) LRES hdr(8) QCFG(72) FMAP(188) FRES hdr(8) + two Huffman chunks with
-  // the reference's own head-room (MaxCompressedSize = n + 359, huffman_enc.cpp:242-244) plus the
-  // per-segment size headers.
-  return 12 + 19 + 136 + 8 + 72 + 188 + 8 + (size_t)g.lres_size + 359 + (size_t)g.planes_bytes + 359 +
-         (size_t)4 * g.rows + 64;
+  // RIFF(12) FRMT(19) LMAP(136) LRES hdr(8) QCFG(72) FMAP(188) FRES hdr(8) + two Huffman chunks.  A
+  // Huffman code over the 261 symbols spends less than log2(261) + 1 < 9.03 bits per token and a token
+  // covers at least one byte, so a chunk of n bytes packs into less than n + n/7 bytes, plus its tree
+  // (<= 359 bytes), one byte of padding and a 2/4-byte header per segment.  (The reference sizes its
+  // buffer as n + 359, huffman_enc.cpp:242-244, which incompressible data can overflow.)
+  const size_t lres = (size_t)g.lres_size, fres = (size_t)g.planes_bytes;
+  return 12 + 19 + 136 + 8 + 72 + 188 + 8 + (lres + lres / 7 + 359 + 8) + (fres + fres / 7 + 359 + (size_t)5 * g.rows) + 64;
 }
 
 size_t himgcu_lres_size(int w, int h, int nch) { return shape_ok(w, h, nch) ? (size_t)make_geom(w, h, nch, nch).lres_size : 0; }
@@ -1159,6 +1202,87 @@ int himgcu_encode_batch(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, int w, 
   return HIMGCU_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Is `p` page-locked host memory (cudaMallocHost / cudaHostRegister / himgcu_host_alloc)?
+bool is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Single-image host calls move up to tens of megabytes through PCIe.  Page-locked caller memory is
+// copied directly (asynchronously, at link speed).  Pageable memory goes through two page-locked
+// staging slots owned by the context, so that the CPU copy of chunk k overlaps the DMA of chunk k-1
+// (a plain cudaMemcpyAsync from pageable memory is staged by the driver in one blocking piece).
+constexpr size_t kStageChunk = (size_t)4 << 20;
+
+int ensure_stage(himgcu_ctx *ctx) {
+  if (!ctx->stage[0]) {
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaMallocHost(&ctx->stage[k], kStageChunk));
+      CK(cudaEventCreateWithFlags(&ctx->stage_ev[k], cudaEventDisableTiming));
+    }
+  }
+  return HIMGCU_OK;
+}
+
+int copy_to_device(himgcu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes <= (64 << 10) || is_pinned(src)) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return HIMGCU_OK;
+  }
+  int rc = ensure_stage(ctx);
+  if (rc) return rc;
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += kStageChunk, k ^= 1) {
+    const size_t m = std::min(kStageChunk, bytes - off);
+    CK(cudaEventSynchronize(ctx->stage_ev[k]));  // the slot's previous DMA is done
+    memcpy(ctx->stage[k], (const char *)src + off, m);
+    CK(cudaMemcpyAsync((char *)dst + off, ctx->stage[k], m, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[k], ctx->stream));
+  }
+  return HIMGCU_OK;
+}
+
+// Device -> host; returns after the data has arrived.
+int copy_to_host(himgcu_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (bytes <= (64 << 10) || is_pinned(dst)) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return HIMGCU_OK;
+  }
+  int rc = ensure_stage(ctx);
+  if (rc) return rc;
+  size_t off_prev = 0, m_prev = 0;
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += kStageChunk, k ^= 1) {
+    const size_t m = std::min(kStageChunk, bytes - off);
+    CK(cudaMemcpyAsync(ctx->stage[k], (const char *)src + off, m, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->stage_ev[k], ctx->stream));
+    if (m_prev) {  // drain the other slot while this chunk is on the wire
+      CK(cudaEventSynchronize(ctx->stage_ev[k ^ 1]));
+      memcpy((char *)dst + off_prev, ctx->stage[k ^ 1], m_prev);
+    }
+    off_prev = off;
+    m_prev = m;
+  }
+  if (m_prev) {
+    CK(cudaEventSynchronize(ctx->stage_ev[k ^ 1]));
+    memcpy((char *)dst + off_prev, ctx->stage[k ^ 1], m_prev);
+  }
+  return HIMGCU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int himgcu_encode(himgcu_ctx *ctx, const uint8_t *pixels, int w, int h, int pixel_stride, int nch, int quality,
                   int use_ycbcr, uint8_t *out, size_t out_cap, size_t *out_size) {
   if (!ctx || !pixels || !out || !out_size) return fail(ctx, HIMGCU_ERR_ARG, "bad argument");
@@ -1174,21 +1298,25 @@ int himgcu_encode(himgcu_ctx *ctx, const uint8_t *pixels, int w, int h, int pixe
   ENSURE("single_in", g.img_bytes, d_in);
   ENSURE("single_out", bound, d_out);
   ENSURE("single_size", sizeof(uint32_t), d_size);
-  CK(cudaMemcpyAsync(d_in, pixels, g.img_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = encode_device(ctx, d_in, 1, g, quality, ycbcr, d_out, bound, d_size);
+  int rc = copy_to_device(ctx, d_in, pixels, g.img_bytes);
   if (rc) return rc;
-  uint32_t size = 0;
-  CK(cudaMemcpyAsync(&size, d_size, sizeof(size), cudaMemcpyDeviceToHost, ctx->stream));
+  rc = encode_device(ctx, d_in, 1, g, quality, ycbcr, d_out, bound, d_size);
+  if (rc) return rc;
+  // one round trip for the size and the encoder's status flag (read = clear)
+  rc = ensure_pinned(ctx, 64);
+  if (rc) return rc;
+  uint32_t *h_size = reinterpret_cast<uint32_t *>(ctx->pinned);
+  int *h_err = reinterpret_cast<int *>(ctx->pinned) + 1, *d_err;
+  ENSURE("enc_err", sizeof(int), d_err);
+  CK(cudaMemcpyAsync(h_size, d_size, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  int err = 0;
-  rc = read_err_flag(ctx, "enc_err", &err);
-  if (rc) return rc;
-  if (err == 5) return fail(ctx, HIMGCU_ERR_UNSUPPORTED, "Huffman code longer than 32 bits");
-  if (err == 99) return fail(ctx, HIMGCU_ERR_CUDA, "internal: packed size mismatch");
-  if (size == 0 || err) return fail(ctx, HIMGCU_ERR_CAPACITY, "internal output bound exceeded");
+  const uint32_t size = *h_size;
+  if ((rc = enc_err_status(ctx, *h_err))) return rc;
+  if (size == 0) return fail(ctx, HIMGCU_ERR_CAPACITY, "internal output bound exceeded");
   if (size > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small: need %u", size);
-  CK(cudaMemcpyAsync(out, d_out, size, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if ((rc = copy_to_host(ctx, out, d_out, size))) return rc;
   *out_size = size;
   return HIMGCU_OK;
 }
@@ -1258,19 +1386,25 @@ int himgcu_decode(himgcu_ctx *ctx, const uint8_t *himg, size_t size, int flags, 
   ENSURE("single_off", sizeof(unsigned long long), d_off);
   ENSURE("single_size", sizeof(uint32_t), d_sz);
   ENSURE("single_status", sizeof(int), d_status);
-  const unsigned long long zero = 0;
-  const uint32_t sz32 = (uint32_t)size;
-  CK(cudaMemcpyAsync(d_in, himg, size, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_off, &zero, sizeof(zero), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(d_sz, &sz32, sizeof(sz32), cudaMemcpyHostToDevice, ctx->stream));
-  int rc = decode_device(ctx, d_in, d_off, d_sz, 1, g, flags, d_px, d_status);
+  int rc = ensure_pinned(ctx, 64);
   if (rc) return rc;
-  int status = 0;
-  CK(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  if (status) return fail(ctx, HIMGCU_REJECT, "stream rejected");
-  CK(cudaMemcpyAsync(out, d_px, g.out_img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  // offset / size / status travel through the context's page-locked scratch (truly asynchronous copies)
+  unsigned long long *h_off = reinterpret_cast<unsigned long long *>(ctx->pinned);
+  uint32_t *h_sz = reinterpret_cast<uint32_t *>(h_off + 1);
+  int *h_status = reinterpret_cast<int *>(h_off + 2);
+  CK(cudaStreamSynchronize(ctx->stream));  // (the scratch words of the previous call are no longer in flight)
+  *h_off = 0;
+  *h_sz = (uint32_t)size;
+  if ((rc = copy_to_device(ctx, d_in, himg, size))) return rc;
+  CK(cudaMemcpyAsync(d_off, h_off, sizeof(*h_off), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d_sz, h_sz, sizeof(*h_sz), cudaMemcpyHostToDevice, ctx->stream));
+  rc = decode_device(ctx, d_in, d_off, d_sz, 1, g, flags, d_px, d_status);
+  if (rc) return rc;
+  // The pixels follow the status on the same stream without a round trip in between: a rejected stream
+  // costs one wasted copy, an accepted one (the common case) saves a synchronisation.
+  CK(cudaMemcpyAsync(h_status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if ((rc = copy_to_host(ctx, out, d_px, g.out_img_bytes))) return rc;
+  if (*h_status) return fail(ctx, HIMGCU_REJECT, "stream rejected");
   return HIMGCU_OK;
 }
 
@@ -1317,7 +1451,8 @@ int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int 
   PipeTrace trace("enc");
   uint64_t pos = 0;
   offsets[0] = 0;
-  return run_pipeline(
+  int failed_image = -1;
+  rc = run_pipeline(
       ctx, K, S,
       [&](int k, int b) -> int {
         const int i0 = k * sub, m = std::min(sub, n - i0);
@@ -1341,7 +1476,10 @@ int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int 
         for (int i = 0; i < m; ++i) {  // the sizes of sub-batch k are on the host
           const uint32_t sz = h_sizes[b][i];
           sizes[i0 + i] = sz;
-          if (sz == 0) return fail(ctx, HIMGCU_ERR_CAPACITY, "image %d could not be encoded", i0 + i);
+          if (sz == 0) {
+            failed_image = i0 + i;
+            return fail(ctx, HIMGCU_ERR_CAPACITY, "image %d could not be encoded", i0 + i);
+          }
           if (pos + sz > out_cap) return fail(ctx, HIMGCU_ERR_CAPACITY, "output buffer too small");
           CK(cudaMemcpyAsync(out + pos, d_out[b] + (size_t)i * stride, sz, cudaMemcpyDeviceToHost, s_out));
           pos += ((uint64_t)sz + 15) & ~15ull;
@@ -1350,6 +1488,29 @@ int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int 
         trace.mark(k, 3, s_out);
         return HIMGCU_OK;
       });
+  // the device flags of the lanes say why an image was not encoded (and catch an internal mismatch even
+  // when every size is non-zero)
+  for (int b = 0; b < S; ++b) {
+    himgcu_ctx *L = lane_of(ctx, b);
+    if (L->bufs.find("enc_err") == L->bufs.end()) continue;
+    int err = 0, r2 = read_err_flag(L, "enc_err", &err);
+    if (r2 == HIMGCU_OK && err && (rc == HIMGCU_OK || failed_image >= 0)) {
+      const int code = enc_err_status(ctx, err);
+      if (failed_image >= 0) ctx->err += " (image " + std::to_string(failed_image) + ")";
+      return code;
+    }
+  }
+  return rc;
+}
+
+int himgcu_encode_status(himgcu_ctx *ctx) {
+  if (!ctx) return HIMGCU_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->bufs.find("enc_err") == ctx->bufs.end()) return HIMGCU_OK;
+  int err = 0;
+  const int rc = read_err_flag(ctx, "enc_err", &err);  // synchronises the stream, clears the flag
+  if (rc) return rc;
+  return enc_err_status(ctx, err);
 }
 
 int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_t *offsets, const uint32_t *sizes,

@@ -549,15 +549,20 @@ __global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_con
   __shared__ uint32_t s_lenx[kSyms];
   __shared__ uint32_t ws[kLayoutThreads / 32 + 1];
   __shared__ unsigned long long s_chunk_bytes[2];
+  __shared__ int s_too_long;
   const int item = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   uint8_t *out = P.out + (size_t)item * P.out_stride;
+  if (t == 0) s_too_long = 0;
 
   // pass 1: segment bit lengths and chunk sizes
   for (int k = 0; k < P.nchunks; ++k) {
     const LayoutChunk &C = P.ch[k];
     const TreeOut *tr = C.trees + item;
     __syncthreads();
-    for (int s = t; s < kSyms; s += blockDim.x) s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+    for (int s = t; s < kSyms; s += blockDim.x) {
+      s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+      if (tr->len[s] > 32) s_too_long = 1;  // the reference's codes are uint32_t (huffman_enc.cpp:179): unsupported
+    }
     if (t == 0) s_chunk_bytes[k] = 0;
     __syncthreads();
     unsigned long long mine = 0;
@@ -584,10 +589,12 @@ __global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_con
   unsigned long long total = 0;
   for (int k = 0; k < P.nchunks; ++k)
     total += (unsigned long long)P.ch[k].prefix_len + ((P.ch[k].trees[item].tree_bits + 7) >> 3) + s_chunk_bytes[k];
-  if (total > P.out_stride || total > 0xffffffffull) {
+  if (s_too_long || total > P.out_stride || total > 0xffffffffull) {
+    // size 0 marks the item as not encoded (the packer skips it, the host calls report it); the flag
+    // says why: 5 = a Huffman code longer than 32 bits, 4 = the output does not fit
     if (t == 0) {
       P.sizes[item] = 0;
-      atomicMax(P.err, 4);
+      atomicMax(P.err, s_too_long ? 5 : 4);
     }
     return;
   }

@@ -53,6 +53,10 @@ int himgcu_reset_stream(himgcu_ctx *ctx);
 int himgcu_synchronize(himgcu_ctx *ctx);
 const char *himgcu_last_error(himgcu_ctx *ctx);
 
+/* FNV-1a (64 bit) of a host buffer: the checksum of SURVEY.md Appendix B, exported so that callers can
+ * compare bitstreams and images with recorded hashes without a second implementation. */
+uint64_t himgcu_fnv1a64(const uint8_t *data, size_t size);
+
 /* Upper bound of an encoded image (same bound as the reference's buffers,
  * huffman_enc.cpp:242-244, encoder.cpp:337-353). */
 size_t himgcu_encode_bound(int width, int height, int num_channels);
@@ -82,6 +86,12 @@ int himgcu_decode(himgcu_ctx *ctx, const uint8_t *himg, size_t size, int flags, 
 int himgcu_encode_batch(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, int width, int height,
                         int num_channels, int quality, int use_ycbcr, uint8_t *d_out,
                         size_t out_stride, uint32_t *d_sizes);
+
+/* Why an image of an earlier asynchronous himgcu_encode_batch call came out with size 0: synchronises
+ * the context's stream and returns (and clears) the encoder's sticky device status -- HIMGCU_OK,
+ * HIMGCU_ERR_CAPACITY (did not fit in out_stride), HIMGCU_ERR_UNSUPPORTED (a Huffman code longer than
+ * the reference's 32-bit code words, huffman_enc.cpp:179) or HIMGCU_ERR_CUDA (internal mismatch). */
+int himgcu_encode_status(himgcu_ctx *ctx);
 
 /* d_himg + d_offsets[i] .. + d_sizes[i] is image i's .himg; every image must have the given
  * shape.  d_status[i] receives HIMGCU_OK / HIMGCU_REJECT per image.  Pixels of image i go to

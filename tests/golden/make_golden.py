@@ -3,7 +3,12 @@
 Run in the build container (needs /root/reference, compiled in place into oracle/_ref by
 oracle/build_oracle.py):   python tests/golden/make_golden.py
 
+    python tests/golden/make_golden.py --shards     (only golden_c4_shards.json)
+
 Outputs (committed):
+  golden_c4_shards.json  the same hashes for the first and the last image of every rank's shard of the
+                       c4 batch (4096 1080p images, seeds 1..4096, quality 50) on 1, 2, 4 and 8 GPUs: what
+                       bench.py checks inside every run, on every rank.
   golden_hashes.json   FNV-1a-64 hashes + sizes of reference .himg output / decoded pixels for the
                        BASELINE.json configurations and edge cases (SURVEY Appendix B generator).
   fixtures.npz         a few small complete reference bitstreams + stage-level vectors.
@@ -56,7 +61,34 @@ FIXTURE_CASES = [
 ]
 
 
+def shard_seeds(total=4096):
+    seeds = set()
+    for world in (1, 2, 4, 8):
+        per = total // world
+        for r in range(world):
+            seeds.update((1 + r * per, (r + 1) * per))
+    return sorted(seeds)
+
+
+def shard_hashes():
+    P, R = oracle.port(), oracle.ref()
+    out = []
+    for seed in shard_seeds():
+        img = P.synth(1920, 1080, 3, seed, 6)
+        packed = R.encode(img, 50, True)
+        dec = R.decode(packed, 1)
+        assert dec is not None
+        out.append({"w": 1920, "h": 1080, "nch": 3, "quality": 50, "seed": seed, "amp": 6, "ycbcr": 1,
+                    "himg_size": len(packed), "himg_hash": f"{P.fnv(np.frombuffer(packed, np.uint8)):016x}",
+                    "pixel_hash": f"{P.fnv(dec):016x}"})
+        print(out[-1])
+    with open(os.path.join(HERE, "golden_c4_shards.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
+    if "--shards" in sys.argv:
+        return shard_hashes()
     P, R = oracle.port(), oracle.ref()
     hashes = []
     for (w, h, n, q, seed, amp, yc) in HASH_CASES:
