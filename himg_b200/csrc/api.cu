@@ -667,7 +667,9 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   }
   LAUNCH("k_huff_tree", k_huff_tree, dim3(n, nchunks), kTreeThreads, 0, TP, d_err);
   LAUNCH("k_huff_layout", k_huff_layout, n, kLayoutThreads, 0, P);
-  const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);  // (below the 48 KiB that need no opt-in)
+  const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);
+  if (ctx->force_generic)  // static + dynamic shared memory of the first-generation packer exceed 48 KiB
+    CK(cudaFuncSetAttribute(k_huff_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)win_bytes));
   for (int k = 0; k < nchunks; ++k) {
     const HuffGeom &hg = chunks[k].hg;
     dim3 grid(hg.nseg * hg.nsub, n);
@@ -1162,8 +1164,9 @@ int himgcu_synchronize(himgcu_ctx *ctx) {
 const char *himgcu_last_error(himgcu_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 uint64_t himgcu_fnv1a64(const uint8_t *data, size_t size) {
-  uint64_t h = 0xcbf29ce484222325ull;
-  for (size_t i = 0; i < size; ++i) h = (h ^ data[i]) * 0x100000001b3ull;
+  // offset basis exactly as in SURVEY.md Appendix B (the recorded reference hashes were made with it)
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < size; ++i) h = (h ^ data[i]) * 1099511628211ull;
   return h;
 }
 

@@ -53,8 +53,9 @@ int himgcu_reset_stream(himgcu_ctx *ctx);
 int himgcu_synchronize(himgcu_ctx *ctx);
 const char *himgcu_last_error(himgcu_ctx *ctx);
 
-/* FNV-1a (64 bit) of a host buffer: the checksum of SURVEY.md Appendix B, exported so that callers can
- * compare bitstreams and images with recorded hashes without a second implementation. */
+/* The checksum of SURVEY.md Appendix B over a host buffer (FNV-1a, 64 bit, with the appendix's offset
+ * basis 1469598103934665603), exported so that callers can compare bitstreams and images with the
+ * recorded reference hashes without a second implementation. */
 uint64_t himgcu_fnv1a64(const uint8_t *data, size_t size);
 
 /* Upper bound of an encoded image (same bound as the reference's buffers,
