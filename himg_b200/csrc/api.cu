@@ -29,6 +29,13 @@ using namespace himgcu;
 
 namespace {
 
+// dst may be page-locked host memory (unified addressing): the stores are visible to the host once an
+// event recorded after the kernel has completed.
+__global__ void k_store_u32(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
 struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
@@ -51,7 +58,7 @@ struct himgcu_ctx {
   // The host-buffer batch calls keep up to kMaxLanes sub-batches in flight.  Lane 0 is this context;
   // lanes 1.. are child contexts (own stream, own workspace) so that the latency-bound kernels of one
   // sub-batch (tree construction, the low-res chunk) overlap the wide kernels of its neighbours.
-  static constexpr int kMaxLanes = 4;
+  static constexpr int kMaxLanes = 8;
   std::vector<himgcu_ctx *> lanes;
   int host_lanes = 3;
   cudaEvent_t ev_in[kMaxLanes] = {}, ev_cmp[kMaxLanes] = {}, ev_out[kMaxLanes] = {};
@@ -70,7 +77,7 @@ struct himgcu_ctx {
   std::vector<std::string> prof_names;
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
-  size_t host_sub_bytes = (size_t)64 << 20;  // staged bytes per sub-batch of the host-buffer calls
+  size_t host_sub_bytes = (size_t)192 << 20;  // staged bytes per sub-batch of the host-buffer calls (measured best: 128-192 MB)
   bool force_generic = false;  // tests: route everything through the generic kernels
   int xform_variant = 0;       // experiments: 0 = newest fast kernels, 1 = previous generation
   // small table uploads are cached by key so that steady-state calls issue no host sync
@@ -879,8 +886,10 @@ extern "C" void himgcu_destroy(himgcu_ctx *ctx);
 namespace {
 
 // One copy queue per direction and device, shared by every context of the process: transfers of
-// concurrent contexts (say one encoding, one decoding) then run in issue order.  Separate streams
-// were observed to starve each other for whole calls on the copy engines.
+// concurrent contexts (say one encoding, one decoding) then run in issue order.  A copy engine keeps
+// serving the stream that keeps feeding it: with separate streams a one-megabyte copy of one call was
+// measured to wait 30 ms until the other call's stream of 100 MB copies had drained (and for the same
+// reason NO copy may be issued on a coding lane's own stream, see the size read-back of the encoder).
 struct CopyQueues {
   cudaStream_t in = nullptr, out = nullptr;
 };
@@ -992,6 +1001,7 @@ int prepare_lanes(himgcu_ctx *ctx, int K, int *count) {
   return HIMGCU_OK;
 }
 himgcu_ctx *lane_of(himgcu_ctx *ctx, int b) { return b == 0 ? ctx : ctx->lanes[b - 1]; }
+
 int finish_lanes(himgcu_ctx *ctx, int S) {
   for (int b = 0; b < S; ++b) CK(cudaStreamSynchronize(lane_of(ctx, b)->stream));
   for (himgcu_ctx *l : ctx->lanes) {
@@ -1009,7 +1019,7 @@ int finish_lanes(himgcu_ctx *ctx, int S) {
 // of one thread encoding and another decoding (both PCIe directions in use).
 // With pageable host memory the copies degrade to synchronous ones but stay correct.
 template <class FIn, class FRun, class FOut>
-int run_pipeline_steps(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy_out) {
+int run_pipeline_steps(himgcu_ctx *ctx, int K, int S, cudaStream_t q_in, cudaStream_t q_out, FIn copy_in, FRun run, FOut copy_out) {
   int n_in = 0, n_run = 0, n_out = 0;  // sub-batches copied in / launched / drained so far
   auto done = [&](cudaEvent_t e, bool *ok) -> int {
     const cudaError_t q = cudaEventQuery(e);
@@ -1025,7 +1035,7 @@ int run_pipeline_steps(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOu
       if ((rc = done(ctx->ev_cmp[b], &ok))) return rc;
       if (ok) {
         if ((rc = copy_out(n_out, b))) return rc;
-        CK(cudaEventRecord(ctx->ev_out[b], ctx->out_stream));
+        CK(cudaEventRecord(ctx->ev_out[b], q_out));
         ++n_out;
         progressed = true;
       }
@@ -1048,7 +1058,7 @@ int run_pipeline_steps(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOu
     if (n_in < K && n_in < n_out + S && n_in < n_run + 2) {  // slot free -> copy in (at most 2 ahead)
       const int b = n_in % S;
       if ((rc = copy_in(n_in, b))) return rc;
-      CK(cudaEventRecord(ctx->ev_in[b], ctx->in_stream));
+      CK(cudaEventRecord(ctx->ev_in[b], q_in));
       ++n_in;
       progressed = true;
     }
@@ -1062,13 +1072,13 @@ int run_pipeline_steps(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOu
 // write into the caller's buffers): drain everything before the caller sees the error and may free or
 // reuse its buffers.
 template <class FIn, class FRun, class FOut>
-int run_pipeline(himgcu_ctx *ctx, int K, int S, FIn copy_in, FRun run, FOut copy_out) {
-  const int rc = run_pipeline_steps(ctx, K, S, copy_in, run, copy_out);
+int run_pipeline(himgcu_ctx *ctx, int K, int S, cudaStream_t q_in, cudaStream_t q_out, FIn copy_in, FRun run, FOut copy_out) {
+  const int rc = run_pipeline_steps(ctx, K, S, q_in, q_out, copy_in, run, copy_out);
   if (rc != HIMGCU_OK) {
     const std::string why = ctx->err;
     for (int b = 0; b < S; ++b) cudaStreamSynchronize(lane_of(ctx, b)->stream);
-    cudaStreamSynchronize(ctx->in_stream);
-    cudaStreamSynchronize(ctx->out_stream);
+    cudaStreamSynchronize(q_in);
+    cudaStreamSynchronize(q_out);
     finish_lanes(ctx, S);
     cudaGetLastError();
     ctx->err = why;
@@ -1456,7 +1466,7 @@ int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int 
   offsets[0] = 0;
   int failed_image = -1;
   rc = run_pipeline(
-      ctx, K, S,
+      ctx, K, S, s_in, s_out,
       [&](int k, int b) -> int {
         const int i0 = k * sub, m = std::min(sub, n - i0);
         trace.mark(k, 0, s_in);
@@ -1469,8 +1479,12 @@ int himgcu_encode_batch_host(himgcu_ctx *ctx, const uint8_t *pixels, int n, int 
         trace.launched(k);
         int r = encode_device(L, d_in[b], m, g, quality, ycbcr, d_out[b], stride, d_sizes[b]);
         if (r) return r;
-        if (cudaMemcpyAsync(h_sizes[b], d_sizes[b], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream) != cudaSuccess)
-          return fail(L, HIMGCU_ERR_CUDA, "size read-back failed");
+        // The sizes reach the host by a KERNEL that stores them into the page-locked array, not by a copy on
+        // the lane's stream: a device-to-host copy from this stream was measured to wait for tens of
+        // milliseconds while another context (a decode call in another thread) kept the copy engine of
+        // that direction busy from its own stream.
+        k_store_u32<<<(m + 255) / 256, 256, 0, L->stream>>>(h_sizes[b], d_sizes[b], m);
+        if (cudaGetLastError() != cudaSuccess) return fail(L, HIMGCU_ERR_CUDA, "size read-back failed");
         trace.mark(k, 2, L->stream);
         return HIMGCU_OK;
       },
@@ -1566,7 +1580,7 @@ int himgcu_decode_batch_host(himgcu_ctx *ctx, const uint8_t *himg, const uint64_
   for (int b = 0; b < S; ++b) CK(cudaStreamSynchronize(lane_of(ctx, b)->stream));
   PipeTrace trace("dec");
   rc = run_pipeline(
-      ctx, K, S,
+      ctx, K, S, s_in, s_out,
       [&](int k, int b) -> int {
         const int i0 = k * sub, m = std::min(sub, n - i0);
         for (int i = 0; i < m; ++i) rel[i0 + i] = offsets[i0 + i] - lo[k];

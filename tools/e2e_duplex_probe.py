@@ -7,7 +7,7 @@ import numpy as np, torch
 import himg_b200
 from himg_b200.synth import synth_images
 
-W, H, NCH, Q, B, CH = 1920, 1080, 3, 50, 128, int(sys.argv[1]) if len(sys.argv) > 1 else 4
+W, H, NCH, Q, B, CH = 1920, 1080, 3, 50, int(__import__("os").environ.get("PROBE_B", "128")), int(sys.argv[1]) if len(sys.argv) > 1 else 4
 dev = torch.device("cuda:0")
 import os
 ctx_e, ctx_d = himg_b200.Context(0), himg_b200.Context(0)
