@@ -254,6 +254,9 @@ def main():
     ctx = himg_b200.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream)
+    # one launch of every kernel per step even for the 4096-image shard of N=1 (the default workspace limit
+    # of 24 GB would split it into two sub-batches): the roofline figures are per launch
+    ctx.set_option("max_workspace_bytes", 48 << 30)
 
     total_images = args.images
     first, B = sharding.shard_range(total_images, world, rank)  # contiguous image ranges per GPU

@@ -544,10 +544,11 @@ int launch_inv4(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, in
   LAUNCH("k_inv_tables", k_inv_tables, ntab, 256, 0, d_tabs, tab_stride, d_inv);
   const unsigned long long inv_stride = tab_stride ? sizeof(InvTables) : 0;
   const int total_pairs = g.rows * (g.cols / 2);
-  dim3 grid((total_pairs + kInv4Threads - 1) / kInv4Threads, 1, n);
-  const int smem = NCH * 64 * 2 * kInv4Threads + 16 * 256 * 2 + 2 * 64 * 4;
-  CK(cudaFuncSetAttribute((k_inverse4<NCH>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  LAUNCH("k_inverse", (k_inverse4<NCH>), grid, kInv4Threads, smem, d_planes, d_R, g, d_inv, inv_stride, d_pixels);
+  constexpr int TP = NCH == 1 ? kInv4ThreadsGray : kInv4ThreadsRgb;
+  dim3 grid((total_pairs + TP - 1) / TP, 1, n);
+  const int smem = NCH * 64 * 2 * TP + kInvTableBytes;
+  CK(cudaFuncSetAttribute((k_inverse4<NCH, TP>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  LAUNCH("k_inverse", (k_inverse4<NCH, TP>), grid, TP, smem, d_planes, d_R, g, d_inv, inv_stride, d_pixels);
   return HIMGCU_OK;
 }
 

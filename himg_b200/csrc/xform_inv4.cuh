@@ -33,7 +33,10 @@
 
 namespace himgcu {
 
-constexpr int kInv4Threads = 256;  // 8 warps, each with its own tile of 32 block pairs
+// Block pairs (= threads) per CTA.  Two CTAs of 256 threads per SM leave 128 registers per thread.  (Nine
+// warps of RGB would still fit the shared memory of an SM -- 110 592 bytes of codes + 4 608 of tables is
+// exactly half of it -- but at the 96 registers that leaves the kernel measured 17 % slower.)
+constexpr int kInv4ThreadsRgb = 256, kInv4ThreadsGray = 256;
 
 // 8-point sequency-ordered WHT on lane pairs whose bias is B on entry, followed by a floor shift by
 // SH (0: none).  The bias on exit is 8 * B >> SH; no lane may leave 16 bits before the shift.
@@ -75,33 +78,60 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 
 // Dequantisation tables of one image, built once per image by k_inv_tables and copied into shared
 // memory by every CTA of K-inv (the tables travel in-band, so they differ from image to image).
-//   dq[s][code] = ((int16)(unmap[code] << s) >> pre) + bias       (quantize.cpp:153-165)
+//   dq[slot(s)][code] = ((int16)(unmap[code] << s) >> pre) + bias       (quantize.cpp:153-165)
+// One table per DISTINCT shift of the image, at most kInvSlots of them (a quality setting uses about five;
+// the shared memory this saves against 16 tables is what lets a CTA of K-inv carry a ninth warp).  An
+// image with more distinct shifts is decoded in OVERFLOW mode: slot 0 holds the plain unmap table, toff
+// holds twice the shifts, and every warp takes the int32 path.
 // When every shift of the image is >= 3 (any quality up to ~60) all coefficients are multiples of 8 and
 // the row pass needs no floor at all: pre = 3, the tables hold value / 8 with a bias of 512 and the row
 // pass skips its shift + mask.  Otherwise pre = 0 and the bias is 4096.
+constexpr int kInvSlots = 8;
 struct alignas(16) InvTables {
-  uint16_t dq[16][256];
+  uint16_t dq[kInvSlots][256];
   uint32_t toff[2][64];  // byte offset of the table of coefficient j (class luma / chroma) inside dq
-  int pre, bias, ycbcr, pad;
+  int pre, bias, ycbcr, overflow;
 };
+constexpr int kInvTableBytes = kInvSlots * 256 * 2 + 2 * 64 * 4;  // what a CTA copies (dq + toff)
 
 // grid n, block 256.  (Shift bytes are masked: a rejected stream leaves its DecTables unspecified.)
 __global__ void k_inv_tables(const DecTables *__restrict__ tabs, unsigned long long tab_stride, InvTables *__restrict__ out) {
+  __shared__ int s_slot[16], s_nslots;
   const DecTables *T = reinterpret_cast<const DecTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.x * tab_stride);
   InvTables *O = out + blockIdx.x;
   const int t = threadIdx.x;
   const int mine = t < 128 ? (T->shift[t >> 6][t & 63] & 15) : 15;
   const bool pre3 = __syncthreads_and(mine >= 3) != 0;
+  // slots of the shifts in use, in increasing order of the shift
+  unsigned used = t < 128 ? 1u << mine : 0u;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) used |= __shfl_xor_sync(0xffffffffu, used, d);
+  if (t < 16) s_slot[t] = 0;
+  if (t == 0) s_nslots = 0;
+  __syncthreads();
+  if ((t & 31) == 0 && t < 128) atomicOr(&s_slot[0], (int)used);  // (s_slot[0] doubles as the mask accumulator)
+  __syncthreads();
+  const unsigned mask = (unsigned)s_slot[0];
+  __syncthreads();
+  if (t < 16) s_slot[t] = __popc(mask & ((1u << t) - 1u));
+  if (t == 0) s_nslots = __popc(mask);
+  __syncthreads();
+  const bool overflow = s_nslots > kInvSlots;
   const int pre = pre3 ? 3 : 0, bias = pre3 ? 512 : 4096;
   const int un = T->full_unmap[t];
-#pragma unroll
-  for (int s = 0; s < 16; ++s) O->dq[s][t] = (uint16_t)(((int)(short)(un << s) >> pre) + bias);
-  if (t < 128) O->toff[t >> 6][t & 63] = (uint32_t)mine * 512u;
+  if (overflow) {
+    O->dq[0][t] = (uint16_t)un;
+  } else {
+    for (int s = 0; s < 16; ++s)
+      if (mask >> s & 1u) O->dq[s_slot[s]][t] = (uint16_t)(((int)(short)(un << s) >> pre) + bias);
+  }
+  // (overflow: twice the shift -- the table gather of the lane-pair path still runs and needs even, in-range offsets)
+  if (t < 128) O->toff[t >> 6][t & 63] = overflow ? (uint32_t)mine * 2u : (uint32_t)s_slot[mine] * 512u;
   if (t == 0) {
     O->pre = pre;
     O->bias = bias;
     O->ycbcr = T->ycbcr != 0 ? 1 : 0;
-    O->pad = 0;
+    O->overflow = overflow ? 1 : 0;
   }
 }
 
@@ -124,14 +154,15 @@ __device__ __forceinline__ void nine2m(uint32_t a, uint32_t b, uint32_t (&t)[9])
 // int32 redo of one channel of a thread's two blocks (some lane of the warp left [-4096, 4095]).
 // Reads the codes again; writes the clamped samples over them.
 __device__ __noinline__ void inv4_wide(uint8_t *cc, int pitch, const uint32_t *tab, uint32_t dq_base, uint32_t top, uint32_t bot,
-                                        int tab_bias, int pre) {
+                                        int tab_bias, int pre, bool overflow) {
 #pragma unroll 1
   for (int blk = 0; blk < 2; ++blk) {
     int y32[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
       const uint32_t code = cc[scan_pos(j) * pitch + blk];
-      y32[j] = (int)(short)(lds_u16(dq_base + tab[j] + 2 * code) - tab_bias) << pre;  // exact: the low bits were zeros
+      if (overflow) y32[j] = (int)(short)((int)(short)lds_u16(dq_base + 2 * code) << (tab[j] >> 1));  // plain unmap table, tab = 2 * shift
+      else y32[j] = (int)(short)(lds_u16(dq_base + tab[j] + 2 * code) - tab_bias) << pre;  // exact: the low bits were zeros
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -160,25 +191,26 @@ __device__ __noinline__ void inv4_wide(uint8_t *cc, int pitch, const uint32_t *t
   }
 }
 
-// grid (ceil(rows * cols / 2 / 256), 1, n), block 256: one tile of 256 consecutive block pairs per CTA.
-// dynamic smem: tile [NCH * 64][512] | dq tables [16][256] u16 | table addresses [2][64] u32
+// grid (ceil(rows * cols / 2 / TP), 1, n), block TP: one tile of TP consecutive block pairs per CTA.
+// dynamic smem: tile [NCH * 64][2 * TP] | dq tables [8][256] u16 | table offsets [2][64] u32
 //
-// The codes of the tile and the image's tables arrive by cp.async (one warp per tile row: 512 contiguous
-// bytes per instruction), the CTA meets at one barrier, then the warps run the three channels and the
+// The codes of the tile and the image's tables arrive by cp.async (the threads of a tile row copy 2 * TP
+// contiguous bytes), the CTA meets at one barrier, then the warps run the three channels and the
 // output phase WITHOUT further barriers: a thread only ever touches its own two byte columns of the tile,
 // and the phases of the inverse load different pipes (LSU in the gather, FMA in the butterflies, ALU in
 // the clamps), so warps that drift apart fill each other's gaps.
 // (Measured and dropped: several tiles per CTA with the next tile prefetched into L2 or copied early from
 // inside the output phase, and tiles owned by single warps -- all slower than fresh CTAs whose start-up
 // overlaps the other resident CTA.)
-template <int NCH>
-__global__ void __launch_bounds__(kInv4Threads, 2)
+template <int NCH, int TP>
+__global__ void __launch_bounds__(TP, 2)
     k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
                const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels) {
   extern __shared__ __align__(128) uint8_t sPl[];
-  constexpr int TP = kInv4Threads, PITCH = 2 * TP;  // pairs per tile, bytes per tile row
+  constexpr int PITCH = 2 * TP, CPR = TP / 8;  // bytes per tile row, 16-byte chunks per tile row
+  static_assert(TP % 32 == 0 && TP == 8 * CPR, "a CTA is 8 groups of one thread per chunk of a tile row");
   uint8_t *sDq = sPl + NCH * 64 * PITCH;
-  uint32_t *sTab = reinterpret_cast<uint32_t *>(sDq + 16 * 256 * 2);
+  uint32_t *sTab = reinterpret_cast<uint32_t *>(sDq + kInvSlots * 256 * 2);
 
   const int t = threadIdx.x;
   const int PR = g.cols >> 1, total = g.rows * PR;
@@ -204,16 +236,16 @@ __global__ void __launch_bounds__(kInv4Threads, 2)
     }
   };
   {
-    // the image's tables (8704 bytes), then the tile: one warp per tile row, one 16-byte chunk (8 pairs of
-    // ONE block row: cols % 16 == 0) per lane
+    // the image's tables, then the tile: thread -> 16-byte chunk t % CPR (8 pairs of ONE block row:
+    // cols % 16 == 0) of the tile rows t / CPR + 8 i; the threads of a row copy 2 * TP contiguous bytes
     const uint4 *tsrc = reinterpret_cast<const uint4 *>(T);
-    for (int i = t; i < (16 * 256 * 2 + 2 * 64 * 4) / 16; i += kInv4Threads) cp_async16(sDq + 16 * i, tsrc + i);
-    const int lane = t & 31, w = t >> 5;
-    if (8 * lane < nact) {
+    for (int i = t; i < kInvTableBytes / 16; i += TP) cp_async16(sDq + 16 * i, tsrc + i);
+    const int cq = t % CPR, r0 = t / CPR;
+    if (8 * cq < nact) {
       int vl, pl;
-      locate(8 * lane, vl, pl);
-      const uint8_t *src = ipl + (size_t)vl * g.seg + 2 * pl + (size_t)w * g.cols;
-      uint8_t *dst = sPl + w * PITCH + lane * 16;
+      locate(8 * cq, vl, pl);
+      const uint8_t *src = ipl + (size_t)vl * g.seg + 2 * pl + (size_t)r0 * g.cols;
+      uint8_t *dst = sPl + r0 * PITCH + cq * 16;
       const size_t rstep = (size_t)8 * g.cols;
 #pragma unroll 8
       for (int i = 0; i < NCH * 8; ++i) {
@@ -223,6 +255,7 @@ __global__ void __launch_bounds__(kInv4Threads, 2)
     }
   }
   const int pre = T->pre, tab_bias = T->bias;
+  const bool overflow = T->overflow != 0;
   const bool pre3 = pre == 3;
   const uint32_t wide_mask = pre3 ? 0xfc00fc00u : 0xe000e000u;  // a lane outside the table's narrow range
   const bool ycbcr = T->ycbcr != 0;
@@ -272,7 +305,7 @@ __global__ void __launch_bounds__(kInv4Threads, 2)
       }
       seen |= (x[j4] | x[j4 + 1]) | (x[j4 + 2] | x[j4 + 3]);  // (two three-input ORs)
     }
-    const bool narrow = __all_sync(0xffffffffu, !active || (seen & wide_mask) == 0);
+    const bool narrow = !overflow && __all_sync(0xffffffffu, !active || (seen & wide_mask) == 0);
     if (narrow) {
       if (pre3) {
 #pragma unroll
@@ -302,7 +335,7 @@ __global__ void __launch_bounds__(kInv4Threads, 2)
         }
       }
     } else {
-      inv4_wide(cc, PITCH, tab, dq_base, tp, bt, tab_bias, pre);
+      inv4_wide(cc, PITCH, tab, dq_base, tp, bt, tab_bias, pre, overflow);
     }
   }
 

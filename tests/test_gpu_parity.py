@@ -366,6 +366,26 @@ def test_stage_inverse_lane_pair_path(ctx, port, shape, kind):
         assert_same(got, want, f"inverse {shape} {kind} q{q} ycbcr={yc}")
 
 
+def test_stage_inverse_many_distinct_shifts(ctx, port):
+    """The lane-pair kernel keeps one dequantisation table per DISTINCT shift, at most eight: a stream whose
+    (in-band) shift tables use more of them is decoded in the kernel's overflow mode (plain unmap table,
+    int32 arithmetic).  Also eight exactly, and small shifts (no pre-division of the tables)."""
+    rng = np.random.default_rng(77)
+    unmap = port.mapfun_parse(port.mapfun_serialize(port.fullres_map_table()))
+    for (w, h, n) in [(640, 48, 3), (1024, 40, 1)]:
+        rows, cols = h >> 3, w >> 3
+        size = rows * cols * 64 * n
+        planes = rng.choice(np.array([0, 0, 0, 0, 1, 255, 2, 254, 3, 253, 9, 247, 30, 226], np.uint8), size)
+        R = rng.integers(0, 256, (n, rows, cols), dtype=np.uint8)
+        for nshift, base in ((12, 0), (8, 3), (16, 0), (9, 3)):
+            sl = ((np.arange(64) * 5) % nshift + base).astype(np.uint8)
+            sc = ((np.arange(64) * 7 + 3) % nshift + base).astype(np.uint8)
+            sl, sc = np.minimum(sl, 15), np.minimum(sc, 15)
+            want = port.fullres_restore(planes, w, h, n, n >= 3, R, sl, sc, unmap)
+            got = ctx.stage_inverse(dev(planes[None]), dev(R[None]), w, h, n, n >= 3, sl, sc, unmap).cpu().numpy()[0]
+            assert_same(got, want, f"inverse {(w, h, n)} with {nshift} distinct shifts from {base}")
+
+
 # ---------------------------------------------------------------------------------------------
 # whole decoder
 # ---------------------------------------------------------------------------------------------
