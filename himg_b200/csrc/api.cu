@@ -18,10 +18,8 @@
 #include "huff_dec_kernels.cuh"
 #include "huff_enc_kernels.cuh"
 #include "tables.h"
-#include "xform_fwd2.cuh"
 #include "xform_fwd3.cuh"
 #include "xform_inv2.cuh"
-#include "xform_inv3.cuh"
 #include "xform_inv4.cuh"
 #include "xform_kernels.cuh"
 
@@ -65,7 +63,7 @@ struct himgcu_ctx {
   std::string err;
   std::map<std::string, DevBuf> bufs;
   DevBuf full_lut;  // 7616-byte |x| -> code LUT, uploaded once
-  DevBuf signed_lut;  // 32 KiB signed LUT (index m + 16384) for k_forward2
+  DevBuf signed_lut;  // 32 KiB signed LUT (index m + 16384) for k_forward3
   void *pinned = nullptr;
   size_t pinned_cap = 0;
   void *stage[2] = {nullptr, nullptr};  // page-locked staging slots of the single-image host calls
@@ -284,7 +282,7 @@ void make_colour(int nch, bool ycbcr, ColourW *cw) {
   }
 }
 
-bool make_quant_recs(const EncodeTables &t, Fwd2Params *P) {
+bool make_quant_recs(const EncodeTables &t, Fwd3Params *P) {
   // value range after the shift: |T| <= 16320, so |m| <= (16320 + round) >> shift
   int half = 1;
   for (int cls = 0; cls < 2; ++cls)
@@ -392,23 +390,6 @@ int launch_fwd(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int
   return HIMGCU_OK;
 }
 
-template <int NCH>
-int launch_fwd2(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
-                const Fwd2Params &P, uint8_t *d_planes) {
-  dim3 grid((g.cols + P.tile_cols - 1) / P.tile_cols, (g.rows + P.tile_rows - 1) / P.tile_rows, n);
-  const int smem = ((2 * P.lut_half + 1 + 15) & ~15) + ((NCH * (P.tile_rows + 1) * (P.tile_cols + 2) + 127) & ~127) +
-                   P.tile_rows * 8 * P.tile_cols * 8 * NCH;
-  const uint8_t *lut = (const uint8_t *)ctx->signed_lut.p;
-  if (ycbcr) {
-    CK(cudaFuncSetAttribute(k_forward2<NCH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LAUNCH("k_forward", (k_forward2<NCH, true>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
-  } else {
-    CK(cudaFuncSetAttribute(k_forward2<NCH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    LAUNCH("k_forward", (k_forward2<NCH, false>), grid, kFwd2Threads, smem, d_pixels, d_L, g, P, lut, d_planes);
-  }
-  return HIMGCU_OK;
-}
-
 template <int NCH, int COLS>
 int launch_fwd3(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
                 const Fwd3Params &P, uint8_t *d_planes) {
@@ -438,14 +419,11 @@ int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, 
   if (!ctx->force_generic && !(ctx->xform_variant & 1) && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
       (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_L) & 1) == 0 &&
       (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
-    Fwd2Params P2;
-    if (make_quant_recs(t, &P2)) {
+    Fwd3Params P;
+    if (make_quant_recs(t, &P)) {
       int rc = upload_signed_lut(ctx);
       if (rc) return rc;
-      Fwd3Params P;
       make_colour(g.nch, t.ycbcr, P.cw);
-      memcpy(P.rec, P2.rec, sizeof(P.rec));
-      P.lut_half = P2.lut_half;
       // plane stride as an immediate for the common widths (1080p, 4K RGB; 8K gray)
       if (g.nch == 3 && g.cols == 240) return launch_fwd3<3, 240>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
       if (g.nch == 3 && g.cols == 480) return launch_fwd3<3, 480>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
@@ -454,27 +432,6 @@ int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, 
         case 1: return launch_fwd3<1, 0>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
         case 3: return launch_fwd3<3, 0>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
         default: return launch_fwd3<4, 0>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
-      }
-    }
-  }
-  if (!ctx->force_generic && g.pstride == g.nch && (g.w % 16) == 0 && (g.h % 8) == 0 &&
-      (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (g.nch == 1 || g.nch == 3 || g.nch == 4)) {
-    Fwd2Params P;
-    if (make_quant_recs(t, &P)) {
-      int rc = upload_signed_lut(ctx);
-      if (rc) return rc;
-      make_colour(g.nch, t.ycbcr, P.cw);
-      // tile: up to 512 blocks per CTA; narrow images stack block rows so the CTA stays full
-      P.tile_cols = std::min(g.cols, kFwd2Blocks);
-      P.tile_rows = std::max(1, std::min(kFwd2Blocks / P.tile_cols, g.rows));
-      if (g.cols > kFwd2Blocks) {  // balance the column tiles
-        const int nt = (g.cols + kFwd2Blocks - 1) / kFwd2Blocks;
-        P.tile_cols = (((g.cols + nt - 1) / nt) + 1) & ~1;
-      }
-      switch (g.nch) {
-        case 1: return launch_fwd2<1>(ctx, d_pixels, d_L, n, g, false, P, d_planes);
-        case 3: return launch_fwd2<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
-        default: return launch_fwd2<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, P, d_planes);
       }
     }
   }
@@ -511,29 +468,6 @@ int launch_inv2(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, in
   return HIMGCU_OK;
 }
 
-template <int NCH, int PITCH>
-int launch_inv3(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
-                const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
-  // balanced column tiles of at most PITCH blocks, multiples of 16 blocks; 512 / PITCH block rows per tile
-  const int nt = (g.cols + PITCH - 1) / PITCH;
-  const int tile_cols = std::min(PITCH, (((g.cols + nt - 1) / nt) + 15) & ~15);
-  constexpr int trows = 512 / PITCH;
-  dim3 grid((g.cols + tile_cols - 1) / tile_cols, (g.rows + trows - 1) / trows, n);
-  const int smem = trows * NCH * 64 * PITCH + 16 * 256 * 2;
-  CK(cudaFuncSetAttribute((k_inverse3<NCH, PITCH>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  LAUNCH("k_inverse", (k_inverse3<NCH, PITCH>), grid, kInv3Threads, smem, d_planes, d_R, g, d_tabs, tab_stride, tile_cols,
-         d_pixels);
-  return HIMGCU_OK;
-}
-
-template <int NCH>
-int launch_inv3_any(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
-                    const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
-  if (g.cols > 128) return launch_inv3<NCH, 256>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
-  if (g.cols > 64) return launch_inv3<NCH, 128>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
-  return launch_inv3<NCH, 64>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
-}
-
 template <int NCH>
 int launch_inv4(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
                 const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
@@ -560,11 +494,6 @@ int stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, 
       (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_R) & 1) == 0) {
     if (g.nch == 1) return launch_inv4<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
     return launch_inv4<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
-  }
-  if (!ctx->force_generic && (g.h % 8) == 0 && (g.cols % 16) == 0 && (g.w % 16) == 0 && (g.nch == 1 || g.nch == 3) &&
-      (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0) {
-    if (g.nch == 1) return launch_inv3_any<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
-    return launch_inv3_any<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
   }
   if (!ctx->force_generic && (g.w % 8) == 0 && (g.h % 8) == 0 && (g.cols % 16) == 0 &&
       (reinterpret_cast<uintptr_t>(d_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_pixels) & 7) == 0 &&

@@ -31,7 +31,7 @@
 #include <utility>
 
 #include "common.cuh"
-#include "xform_fwd2.cuh"  // lane-pair helpers, TMA / mbarrier wrappers, ColourW, QuantRec
+#include "xform_lane.cuh"  // lane-pair helpers, TMA / mbarrier wrappers, ColourW, QuantRec
 
 namespace himgcu {
 

@@ -18,17 +18,12 @@
 #define HIMG_B200_XFORM_INV2_CUH_
 
 #include "common.cuh"
+#include "xform_lane.cuh"  // cp_async16
 
 namespace himgcu {
 
 constexpr int kInv2Threads = 256;
 constexpr int kInv2Pitch = 256;  // bytes per staged plane row = max blocks per tile
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // grid (ceil(cols/tile_cols), rows, n), block 256.
 // dynamic smem: planes tile [NCH*64][256] | sOut [NCH][256][17] words

@@ -27,9 +27,7 @@
 #define HIMG_B200_XFORM_INV4_CUH_
 
 #include "common.cuh"
-#include "xform_fwd2.cuh"  // mid2 / nine2 / smem_u32
-#include "xform_inv2.cuh"  // cp_async16
-#include "xform_inv3.cuh"  // iwht8p
+#include "xform_lane.cuh"  // mid2 / nine2 / ibfly / smem_u32 / cp_async16
 
 namespace himgcu {
 
