@@ -68,6 +68,27 @@ __device__ __forceinline__ void iwht8q(uint32_t &x0, uint32_t &x1, uint32_t &x2,
   }
 }
 
+// 8-point sequency-ordered WHT on lane pairs WITHOUT bias constants: a packed word is the 32-bit integer
+// hi * 65536 + lo with SIGNED fields, sums and differences of such words are exact modulo 2^32 whatever
+// the signs of the fields, and every butterfly is a plain two-input add or subtract that either the ALU
+// or the FMA pipe (IMAD) can execute.  The fields only have to be non-negative where a word is taken
+// apart again (floor shift, DPX clamp); the caller arranges that through the DC input (see the kernel).
+__device__ __forceinline__ void iwht8u(uint32_t &x0, uint32_t &x1, uint32_t &x2, uint32_t &x3, uint32_t &x4, uint32_t &x5,
+                                       uint32_t &x6, uint32_t &x7) {
+  const uint32_t a0 = x0 + x4, a1 = x1 + x5, a2 = x2 + x6, a3 = x3 + x7;
+  const uint32_t a4 = x0 - x4, a5 = x1 - x5, a6 = x2 - x6, a7 = x3 - x7;
+  const uint32_t b0 = a0 + a2, b1 = a1 + a3, b2 = a0 - a2, b3 = a1 - a3;
+  const uint32_t b4 = a4 + a6, b5 = a5 + a7, b6 = a4 - a6, b7 = a5 - a7;
+  x0 = b0 + b1;
+  x1 = b4 + b5;
+  x2 = b6 + b7;
+  x3 = b2 + b3;
+  x4 = b2 - b3;
+  x5 = b6 - b7;
+  x6 = b4 - b5;
+  x7 = b0 - b1;
+}
+
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -133,20 +154,25 @@ __global__ void k_inv_tables(const DecTables *__restrict__ tabs, unsigned long l
   }
 }
 
-// nine2 whose outputs are low-res - 4096 per lane (the addend of the fused add + clamp): the leaves of
-// the midpoint tree take the OR of 0xf000 in the same three-input logic operation as their mask.
-__device__ __forceinline__ void nine2m(uint32_t a, uint32_t b, uint32_t (&t)[9]) {
-  const uint32_t M = 0xf000f000u;
-  const uint32_t t4 = mid2(a, b), t2 = mid2(a, t4), t6 = mid2(t4, b);
-  t[0] = a | M;
-  t[2] = t2 | M;
-  t[4] = t4 | M;
-  t[6] = t6 | M;
-  t[1] = (((a + t2 + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
-  t[3] = (((t2 + t4 + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
-  t[5] = (((t4 + t6 + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
-  t[7] = (((t6 + b + 0x00010001u) >> 1) & 0x00ff00ffu) | M;
-  t[8] = b | M;
+// Nine-tap midpoint interpolation on lane pairs that CARRY the addend of the fused add + clamp: every
+// input and output lane is low-res | 0xf000 (= low-res - 4096 as int16).  The two 0xf000 of a sum always
+// carry out of the low lane, so the rounding constant of the high lane is that carry (C = 1, not
+// 0x00010001); the mask of the shifted sum takes its 0xf000 back in the same three-input logic operation.
+// M = 0xf000f000 in a REGISTER the compiler cannot fold (a logic instruction takes one immediate only:
+// with two immediates the mask and the OR are two instructions).
+__device__ __forceinline__ uint32_t mid2m(uint32_t a, uint32_t b, uint32_t M) {
+  return (((a + b + 1u) >> 1) & 0x00ff00ffu) | M;
+}
+__device__ __forceinline__ void nine2m(uint32_t a, uint32_t b, uint32_t M, uint32_t (&t)[9]) {
+  t[0] = a;
+  t[8] = b;
+  t[4] = mid2m(a, b, M);
+  t[2] = mid2m(a, t[4], M);
+  t[6] = mid2m(t[4], b, M);
+  t[1] = mid2m(a, t[2], M);
+  t[3] = mid2m(t[2], t[4], M);
+  t[5] = mid2m(t[4], t[6], M);
+  t[7] = mid2m(t[6], b, M);
 }
 
 // int32 redo of one channel of a thread's two blocks (some lane of the warp left [-4096, 4095]).
@@ -203,7 +229,7 @@ __device__ __noinline__ void inv4_wide(uint8_t *cc, int pitch, const uint32_t *t
 template <int NCH, int TP>
 __global__ void __launch_bounds__(TP, 2)
     k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
-               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels) {
+               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels, uint32_t one) {
   extern __shared__ __align__(128) uint8_t sPl[];
   constexpr int PITCH = 2 * TP, CPR = TP / 8;  // bytes per tile row, 16-byte chunks per tile row
   static_assert(TP % 32 == 0 && TP == 8 * CPR, "a CTA is 8 groups of one thread per chunk of a tile row");
@@ -254,7 +280,11 @@ __global__ void __launch_bounds__(TP, 2)
   }
   const int pre = T->pre, tab_bias = T->bias;
   const bool overflow = T->overflow != 0;
+#ifdef HIMG_FORCE_PRE3  // (instruction counting only: tools/phase_count.py)
+  const bool pre3 = true;
+#else
   const bool pre3 = pre == 3;
+#endif
   const uint32_t wide_mask = pre3 ? 0xfc00fc00u : 0xe000e000u;  // a lane outside the table's narrow range
   const bool ycbcr = T->ycbcr != 0;
   const bool active = t < nact;
@@ -305,25 +335,39 @@ __global__ void __launch_bounds__(TP, 2)
     }
     const bool narrow = !overflow && __all_sync(0xffffffffu, !active || (seen & wide_mask) == 0);
     if (narrow) {
+      // The table lanes carry a bias B (512 / 4096) and the butterflies add none, so after a pass only
+      // the DC output of each transform is biased (by 8 B per pass).  One constant on the DC input gives
+      // every output of the 2-D transform the same +32768 per lane; the outputs that were biased already
+      // wrap around and take 0x7fff8000 (= 32768 per lane minus the carry of the wrap) afterwards.
       if (pre3) {
+        x[0] += 0x80008000u;
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-          iwht8q<512, 0>(x[r * 8 + 0], x[r * 8 + 1], x[r * 8 + 2], x[r * 8 + 3], x[r * 8 + 4], x[r * 8 + 5], x[r * 8 + 6], x[r * 8 + 7]);
+          iwht8u(x[r * 8 + 0], x[r * 8 + 1], x[r * 8 + 2], x[r * 8 + 3], x[r * 8 + 4], x[r * 8 + 5], x[r * 8 + 6], x[r * 8 + 7]);
       } else {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
           iwht8q<4096, 3>(x[r * 8 + 0], x[r * 8 + 1], x[r * 8 + 2], x[r * 8 + 3], x[r * 8 + 4], x[r * 8 + 5], x[r * 8 + 6], x[r * 8 + 7]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] += 0x80008000u;  // (every lane is floor(..) + 4096 here)
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        iwht8q<4096, 3>(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
+      for (int q = 0; q < 8; ++q) iwht8u(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
+      const uint32_t fixq = pre3 ? 0u : 0x7fff8000u;
+      x[0] += 0x7fff8000u;
+#pragma unroll
+      for (int q = 1; q < 8; ++q) x[q] += fixq;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) x[j] = (x[j] >> 3) & 0x1fff1fffu;
+      const uint32_t M = one * 0xf000f000u;  // (opaque to the compiler: stays in a register)
       uint32_t lf[9], rt[9];
-      nine2(__byte_perm(tp, 0u, 0x4140), __byte_perm(bt, 0u, 0x4140), lf);  // left columns: corners u | u+1
-      nine2(__byte_perm(tp, 0u, 0x4241), __byte_perm(bt, 0u, 0x4241), rt);  // right columns: u+1 | u+2
+      // (the 0xf0 bytes make every lane low-res | 0xf000: see nine2m)
+      nine2m(__byte_perm(tp, 0xf0u, 0x4140), __byte_perm(bt, 0xf0u, 0x4140), M, lf);  // left columns: corners u | u+1
+      nine2m(__byte_perm(tp, 0xf0u, 0x4241), __byte_perm(bt, 0xf0u, 0x4241), M, rt);  // right columns: u+1 | u+2
 #pragma unroll
       for (int y = 0; y < 8; ++y) {
         uint32_t tl[9];
-        nine2m(lf[y], rt[y], tl);
+        nine2m(lf[y], rt[y], M, tl);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           // lane + (low-res - 4096), min 255, max 0: two samples per instruction
@@ -338,35 +382,45 @@ __global__ void __launch_bounds__(TP, 2)
   }
 
   // ---- inverse colour map + interleave + 16-byte stores (a thread reads back its own two columns)
+  // `one` is the number 1 as a kernel argument: a multiplication by a value the compiler cannot see
+  // stays an IMAD, i.e. it runs on the FMA pipe instead of the (fuller) ALU pipe.
   {
     const bool do_colour = ycbcr && NCH >= 3;
+    const uint32_t two = one + one, k256 = one << 8, neg1 = 0u - one;
+    // The unpacking byte-permute gives Y a bias of 512 and Cb one of 256 per lane for free (constant bytes).
+    // With hb = (Cb + 256 + Cr) >> 1 = ((Cb + Cr) >> 1) + 128 and (Cb + Cr + 2) >> 1 = ((Cb + Cr) >> 1) + 1:
+    //   Gp = Y + 512 - hb = G + 257  (positive lanes),  R = Gp + (2 Cr - 512),  B = Gp + (2 (Cb + 256) - 1024)
+    // where 2 Cr - 512 is negative whatever Cr is, so the packed multiply-add never carries between lanes.
+    uint32_t bias[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) bias[c] = !do_colour ? 0u : c == 0 ? 0x02u : c == 1 ? 0x01u : 0u;
 #pragma unroll
     for (int y = 0; y < 8; ++y) {
       uint32_t s[8 * NCH];  // lane pairs in memory order: pixel-major, channel-minor
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        uint32_t ch[NCH];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int c = 0; c < NCH; ++c)
-          ch[c] = __byte_perm((uint32_t) * reinterpret_cast<const uint16_t *>(col + (c * 64 + y * 8 + i) * PITCH), 0u, 0x4140);
-        if (NCH >= 3 && do_colour) {
-          // cb = 2Cb - 255, cr = 2Cr - 255, G = Y - ((cb + cr + 2) >> 2) = Y + 128 - ((Cb + Cr + 2) >> 1)
-          const uint32_t h = ((ch[1] + ch[NCH >= 3 ? 2 : 0] + 0x00020002u) >> 1) & 0x01ff01ffu;
-          const uint32_t G = ch[0] + 0x01800180u - h;                      // G + 256 per lane, positive
-          const uint32_t cr = (ch[NCH >= 3 ? 2 : 0] << 1) + 0xfe01fe01u;   // cr - 256 per lane (int16)
-          const uint32_t cb = (ch[1] << 1) + 0xfe01fe01u;
-          ch[0] = __viaddmin_s16x2_relu(G, cr, 0x00ff00ffu);
-          ch[1] = __viaddmin_s16x2_relu(G, 0xff00ff00u, 0x00ff00ffu);
-          ch[NCH >= 3 ? 2 : 0] = __viaddmin_s16x2_relu(G, cb, 0x00ff00ffu);
-        }
+          s[i * NCH + c] = __byte_perm((uint32_t) * reinterpret_cast<const uint16_t *>(col + (c * 64 + y * 8 + i) * PITCH), bias[c], 0x4140);
+      if (NCH >= 3 && do_colour) {
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) s[i * NCH + c] = ch[c];
+        for (int i = 0; i < 8; ++i) {
+          uint32_t *ch = s + i * NCH;
+          const uint32_t hb = ((ch[1] + ch[NCH >= 3 ? 2 : 0]) >> 1) & 0x01ff01ffu;
+          const uint32_t Gp = hb * neg1 + ch[0];
+          const uint32_t cr = ch[NCH >= 3 ? 2 : 0] * two + 0xfe00fe00u;
+          const uint32_t cb = ch[1] * two + 0xfc00fc00u;
+          ch[0] = __viaddmin_s16x2_relu(Gp, cr, 0x00ff00ffu);
+          ch[1] = __viaddmin_s16x2_relu(Gp, 0xfefffeffu, 0x00ff00ffu);
+          ch[NCH >= 3 ? 2 : 0] = __viaddmin_s16x2_relu(Gp, cb, 0x00ff00ffu);
+        }
       }
-      // words of block A and of block B: four consecutive lane pairs -> one word each
+      // words of block A and of block B: four consecutive lane pairs -> one word each (every lane is a
+      // byte value, so s1 * 256 + s0 = A0 | A1 << 8 | B0 << 16 | B1 << 24)
       uint32_t wa[2 * NCH], wb[2 * NCH];
 #pragma unroll
       for (int m = 0; m < 2 * NCH; ++m) {
-        const uint32_t pq = __byte_perm(s[4 * m], s[4 * m + 1], 0x6240), q = __byte_perm(s[4 * m + 2], s[4 * m + 3], 0x6240);
+        const uint32_t pq = s[4 * m + 1] * k256 + s[4 * m], q = s[4 * m + 3] * k256 + s[4 * m + 2];
         wa[m] = __byte_perm(pq, q, 0x5410);
         wb[m] = __byte_perm(pq, q, 0x7632);
       }

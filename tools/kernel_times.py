@@ -5,6 +5,10 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from himg_b200 import _native  # noqa: E402
+
+if os.environ.get("HIMG_AB_LIB"):  # A/B runs of this tool only: time another build of the library
+    _native.LIB_PATH = os.environ["HIMG_AB_LIB"]
 import himg_b200  # noqa: E402
 from himg_b200.synth import synth_images  # noqa: E402
 
