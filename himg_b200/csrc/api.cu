@@ -75,6 +75,7 @@ struct himgcu_ctx {
   std::vector<std::string> prof_names;
   uint64_t launches = 0;
   size_t max_workspace = (size_t)24 << 30;
+  int item_lists = 1;  // hand the item lists of k_huff_hist2 to the packer (option "item_lists")
   size_t host_sub_bytes = (size_t)192 << 20;  // staged bytes per sub-batch of the host-buffer calls (measured best: 128-192 MB)
   bool force_generic = false;  // tests: route everything through the generic kernels
   int xform_variant = 0;       // experiments: 0 = newest fast kernels, 1 = previous generation
@@ -560,6 +561,7 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   uint32_t *d_part[2];
   TreeParams TP;
   memset(&TP, 0, sizeof(TP));
+  ItemLists lists[2];
   for (int k = 0; k < nchunks; ++k) {
     HuffGeom &hg = chunks[k].hg;
     // Parts per segment: only worth it when the segments alone cannot fill the GPU (the low-res chunk
@@ -583,8 +585,19 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     ENSURE((tag + "_segbits").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_bits[k]);
     ENSURE((tag + "_segpos").c_str(), (size_t)n * hg.nseg * sizeof(uint32_t), d_pos[k]);
     dim3 grid(hg.nseg * hg.nsub, n);
+    // item lists of the pieces, handed from the histogram pass to the packer (see ItemLists)
+    ItemLists &il = lists[k];
+    il = ItemLists{nullptr, nullptr, nullptr, 0};
+    if (!ctx->force_generic && ctx->item_lists) {
+      const int ppp = (hg.sub_size + kTokPiece - 1) / kTokPiece;
+      const size_t slots = (size_t)n * hg.nseg * hg.nsub * ppp;
+      ENSURE((tag + "_itpos").c_str(), slots * kItemCap * sizeof(unsigned short), il.pos);
+      ENSURE((tag + "_itval").c_str(), slots * kItemCap, il.val);
+      ENSURE((tag + "_itcnt").c_str(), slots * sizeof(uint32_t), il.count);
+      il.pieces_per_part = ppp;
+    }
     if (ctx->force_generic) LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
-    else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
+    else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k], il);
     TP.seghist[k] = d_seghist[k];
     TP.trees[k] = d_trees[k];
     TP.rows[k] = hg.nseg * hg.nsub;
@@ -615,7 +628,7 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
              d_pos[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
     else
       LAUNCH("k_huff_pack", k_huff_pack3, grid, kTokThreads, 0, chunks[k].d_in, hg, d_trees[k], d_bits[k], d_pos[k],
-             d_part[k], d_sizes, d_out, (unsigned long long)out_stride, d_err);
+             d_part[k], d_sizes, d_out, (unsigned long long)out_stride, d_err, lists[k]);
     if (hg.nseg > 1) {
       const long long tot = (long long)n * hg.nseg;
       LAUNCH("k_huff_stale", k_huff_stale, (unsigned)((tot + 255) / 256), 256, 0, n, hg.nseg, d_bits[k], d_pos[k],
@@ -644,7 +657,10 @@ int enc_err_status(himgcu_ctx *ctx, int err) {
 
 size_t per_image_encode_ws(const Geom &g) {
   return 2 * (size_t)g.nch * g.rows * g.cols + g.lres_stride + g.planes_bytes +
-         (size_t)(g.rows + 1) * kSyms * 4 + 2 * sizeof(TreeOut) + (size_t)(g.rows + 1) * 8;
+         (size_t)(g.rows + 1) * kSyms * 4 + 2 * sizeof(TreeOut) + (size_t)(g.rows + 1) * 8 +
+         // item lists: 3 bytes x kItemCap per 8 KiB piece of the planes and of the low-res chunk
+         ((size_t)g.rows * ((g.seg + kTokPiece - 1) / kTokPiece) + (g.lres_size + kTokPiece - 1) / kTokPiece + 64) *
+             (kItemCap * 3 + 4);
 }
 
 // Whole-image encode of a sub-batch already resident on the device.
@@ -1698,6 +1714,7 @@ int himgcu_set_option(himgcu_ctx *ctx, const char *name, long long value) {
   if (!strcmp(name, "force_generic")) ctx->force_generic = value != 0;
   else if (!strcmp(name, "xform_variant")) ctx->xform_variant = (int)value;
   else if (!strcmp(name, "max_workspace_bytes")) ctx->max_workspace = (size_t)value;
+  else if (!strcmp(name, "item_lists")) ctx->item_lists = value != 0;
   else if (!strcmp(name, "host_sub_batch_bytes")) ctx->host_sub_bytes = (size_t)std::max<long long>(value, 1 << 20);
   else if (!strcmp(name, "host_lanes")) ctx->host_lanes = (int)std::max<long long>(1, std::min<long long>(value, himgcu_ctx::kMaxLanes));
   else return fail(ctx, HIMGCU_ERR_ARG, "unknown option %s", name);

@@ -299,9 +299,27 @@ __device__ __forceinline__ void atomic_or_byte(uint8_t *p, uint32_t v) {
   atomicOr(reinterpret_cast<uint32_t *>(a & ~(uintptr_t)3), (v & 0xffu) << (8 * (a & 3)));
 }
 
+// Item lists handed from the histogram pass to the packer.  Both kernels cut a part into the same 8 KiB
+// pieces and need the same list of non-zero bytes per piece; building it (load, non-zero masks, block
+// scan, compaction) was 40 % of the packer's time.  k_huff_hist2 therefore stores the list of every
+// piece that holds at most kItemCap items (position inside the piece + byte value: 3 bytes per item,
+// ~0.4 bytes per coefficient byte at quality 50) and the packer reads it back instead of the planes.
+// Denser pieces are marked and rebuilt from the planes as before.
+constexpr int kItemCap = 2048;
+constexpr uint32_t kItemsNotStored = 0xffffffffu;
+struct ItemLists {
+  unsigned short *pos;  // [slots][kItemCap]
+  uint8_t *val;         // [slots][kItemCap]
+  uint32_t *count;      // [slots]; kItemsNotStored: rebuild from the planes
+  int pieces_per_part;  // slots of one (item, segment, part); 0: no lists (every piece is rebuilt)
+};
+__device__ __forceinline__ size_t item_slot(const ItemLists &L, const HuffGeom &hg, int item, int piece) {
+  return ((size_t)item * hg.nseg * hg.nsub + blockIdx.x) * L.pieces_per_part + piece;
+}
+
 // grid (nseg * nsub, n), block kTokThreads.  seghist: [n][nseg * nsub][261].
 __global__ void __launch_bounds__(kTokThreads, 8)
-    k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist) {
+    k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist, ItemLists lists) {
   __shared__ uint32_t sh[kSyms];
   __shared__ uint32_t ws[kTokWarps + 1];
   __shared__ uint32_t rows[kTokThreads * kRowWords];
@@ -317,6 +335,9 @@ __global__ void __launch_bounds__(kTokThreads, 8)
   for (int base = 0; base < plen; base += kTokPiece) {
     PieceItems P;
     carry = build_items(seg, plen, base, rows, ipos, ws, carry, &P);
+    const bool keep = lists.pieces_per_part != 0 && P.count <= kItemCap;
+    const size_t slot = lists.pieces_per_part ? item_slot(lists, hg, blockIdx.y, base / kTokPiece) : 0;
+    if (lists.pieces_per_part && threadIdx.x == 0) lists.count[slot] = keep ? (uint32_t)P.count : kItemsNotStored;
     for (int k = threadIdx.x; k < P.count; k += kTokThreads) {
       uint32_t z = item_gap(ipos, k, P.zeros_in), ex;
       while (z >= (uint32_t)kMaxRun) {
@@ -324,7 +345,12 @@ __global__ void __launch_bounds__(kTokThreads, 8)
         z -= kMaxRun;
       }
       if (z) atomicAdd(&sh[run_symbol(z, &ex)], 1u);
-      atomicAdd(&sh[item_byte(rows, ipos[k])], 1u);
+      const uint32_t v = item_byte(rows, ipos[k]);
+      atomicAdd(&sh[v], 1u);
+      if (keep) {
+        lists.pos[slot * kItemCap + k] = ipos[k];
+        lists.val[slot * kItemCap + k] = (uint8_t)v;
+      }
     }
     __syncthreads();  // rows / ipos are rewritten by the next piece
   }
@@ -825,13 +851,13 @@ __global__ void __launch_bounds__(kTokThreads, kP3MinCtas)
     k_huff_pack3(const uint8_t *__restrict__ in, HuffGeom hg, const TreeOut *__restrict__ trees,
                  const uint32_t *__restrict__ seg_bits, const uint32_t *__restrict__ seg_pos,
                  const uint32_t *__restrict__ part_start, const uint32_t *__restrict__ sizes,
-                 uint8_t *__restrict__ out, unsigned long long out_stride, int *err) {
+                 uint8_t *__restrict__ out, unsigned long long out_stride, int *err, ItemLists lists) {
   __shared__ uint32_t win[kWin2Words + 4];
   __shared__ uint2 s_tab[kSyms];
   __shared__ int s_last;
   __shared__ uint32_t ws[kTokWarps + 1];
   __shared__ uint32_t s_half;
-  __shared__ uint32_t rows[kTokThreads * kRowWords];
+  __shared__ __align__(16) uint32_t rows[kTokThreads * kRowWords];
   __shared__ __align__(16) unsigned short ipos[kTokPiece + 8];
   const int item = blockIdx.y, t = threadIdx.x;
   const int b = blockIdx.x / hg.nsub, part = blockIdx.x - b * hg.nsub;
@@ -893,9 +919,31 @@ __global__ void __launch_bounds__(kTokThreads, kP3MinCtas)
     }
   };
 
+  uint8_t *ival = reinterpret_cast<uint8_t *>(rows);  // byte values of a stored list (the rows are not needed then)
   for (int base = 0; base < plen; base += kTokPiece) {
     PieceItems P;
-    carry = build_items(seg, plen, base, rows, ipos, ws, carry, &P);
+    bool from_list = false;
+    if (lists.pieces_per_part) {
+      const size_t slot = item_slot(lists, hg, item, base / kTokPiece);
+      const uint32_t cnt = lists.count[slot];
+      if (cnt != kItemsNotStored) {
+        // the list of k_huff_hist2: 16 / 8 bytes per thread and step, then one barrier
+        from_list = true;
+        const uint4 *gp = reinterpret_cast<const uint4 *>(lists.pos + slot * kItemCap);
+        const uint2 *gv = reinterpret_cast<const uint2 *>(lists.val + slot * kItemCap);
+        for (uint32_t i = t; i * 8 < cnt; i += kTokThreads) {
+          reinterpret_cast<uint4 *>(ipos)[i] = __ldg(gp + i);
+          reinterpret_cast<uint2 *>(ival)[i] = __ldg(gv + i);
+        }
+        __syncthreads();
+        P.count = (int)cnt;
+        P.len = min(kTokPiece, plen - base);
+        P.zeros_in = carry;
+        carry = cnt ? (uint32_t)(P.len - 1 - (int)ipos[cnt - 1]) : carry + (uint32_t)P.len;
+      }
+    }
+    if (!from_list) carry = build_items(seg, plen, base, rows, ipos, ws, carry, &P);
+    auto byte_of = [&](int k, int pos) -> uint32_t { return from_list ? (uint32_t)ival[k] : item_byte(rows, pos); };
     // a first gap of 16662 zeros or more: its maximal tokens go out first, the remainder stays with item 0
     uint32_t gap0_cut = 0;
     if (P.count > 0) {
@@ -925,7 +973,7 @@ __global__ void __launch_bounds__(kTokThreads, kP3MinCtas)
             uint32_t gap = (uint32_t)(pos - prev - 1);
             if (k0 + j == 0) gap += P.zeros_in - gap0_cut;
             prev = pos;
-            const uint2 lr = s_tab[item_byte(rows, pos)];
+            const uint2 lr = s_tab[byte_of(k0 + j, pos)];
             uint64_t tk = lr.x;
             uint32_t l = lr.y & 255u;
             if (gap) {
@@ -980,7 +1028,7 @@ __global__ void __launch_bounds__(kTokThreads, kP3MinCtas)
                 if (tl[j] <= 64) {
                   put64(win, pos, tok[j], tl[j]);
                 } else {  // run token, then the literal
-                  const uint2 lr = s_tab[item_byte(rows, (int)ipos[k0 + j])];
+                  const uint2 lr = s_tab[byte_of(k0 + j, (int)ipos[k0 + j])];
                   const uint32_t rb = tl[j] - (lr.y & 255u);
                   put64(win, pos, tok[j], rb);
                   put64(win, pos + rb, lr.x, lr.y & 255u);
