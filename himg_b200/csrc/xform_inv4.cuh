@@ -215,98 +215,35 @@ __device__ __noinline__ void inv4_wide(uint8_t *cc, int pitch, const uint32_t *t
   }
 }
 
-// grid (ceil(rows * cols / 2 / TP), 1, n), block TP: one tile of TP consecutive block pairs per CTA.
-// dynamic smem: tile [NCH * 64][2 * TP] | dq tables [8][256] u16 | table offsets [2][64] u32
-//
-// The codes of the tile and the image's tables arrive by cp.async (the threads of a tile row copy 2 * TP
-// contiguous bytes), the CTA meets at one barrier, then the warps run the three channels and the
-// output phase WITHOUT further barriers: a thread only ever touches its own two byte columns of the tile,
-// and the phases of the inverse load different pipes (LSU in the gather, FMA in the butterflies, ALU in
-// the clamps), so warps that drift apart fill each other's gaps.
-// (Measured and dropped: several tiles per CTA with the next tile prefetched into L2 or copied early from
-// inside the output phase, and tiles owned by single warps -- all slower than fresh CTAs whose start-up
-// overlaps the other resident CTA.)
-template <int NCH, int TP>
-__global__ void __launch_bounds__(TP, 2)
-    k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
-               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels, uint32_t one) {
-  extern __shared__ __align__(128) uint8_t sPl[];
-  constexpr int PITCH = 2 * TP, CPR = TP / 8;  // bytes per tile row, 16-byte chunks per tile row
-  static_assert(TP % 32 == 0 && TP == 8 * CPR, "a CTA is 8 groups of one thread per chunk of a tile row");
-  uint8_t *sDq = sPl + NCH * 64 * PITCH;
-  uint32_t *sTab = reinterpret_cast<uint32_t *>(sDq + kInvSlots * 256 * 2);
-
-  const int t = threadIdx.x;
-  const int PR = g.cols >> 1, total = g.rows * PR;
-  const int f0 = blockIdx.x * TP;
-  const int nact = min(TP, total - f0);
-  const uint8_t *ipl = planes + (size_t)blockIdx.z * g.planes_bytes;
-  uint8_t *img = pixels + (size_t)blockIdx.z * g.out_img_bytes;
-  const InvTables *T = reinterpret_cast<const InvTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tab_stride);
-  // block row / first pair of the tile's first element: one division per CTA, everything else by
-  // carrying (a tile spans few block rows unless the image is very narrow)
-  const int v0 = f0 / PR, p0 = f0 - v0 * PR;
-  auto locate = [&](int k, int &v, int &p) {  // element f0 + k of the image -> block row, pair in the row
-    if (PR >= 32) {
-      v = v0;
-      p = p0 + k;
-      while (p >= PR) {
-        p -= PR;
-        ++v;
-      }
-    } else {
-      v = (f0 + k) / PR;
-      p = f0 + k - v * PR;
-    }
-  };
-  {
-    // the image's tables, then the tile: thread -> 16-byte chunk t % CPR (8 pairs of ONE block row:
-    // cols % 16 == 0) of the tile rows t / CPR + 8 i; the threads of a row copy 2 * TP contiguous bytes
-    const uint4 *tsrc = reinterpret_cast<const uint4 *>(T);
-    for (int i = t; i < kInvTableBytes / 16; i += TP) cp_async16(sDq + 16 * i, tsrc + i);
-    const int cq = t % CPR, r0 = t / CPR;
-    if (8 * cq < nact) {
-      int vl, pl;
-      locate(8 * cq, vl, pl);
-      const uint8_t *src = ipl + (size_t)vl * g.seg + 2 * pl + (size_t)r0 * g.cols;
-      uint8_t *dst = sPl + r0 * PITCH + cq * 16;
-      const size_t rstep = (size_t)8 * g.cols;
-#pragma unroll 8
-      for (int i = 0; i < NCH * 8; ++i) {
-        cp_async16(dst + i * 8 * PITCH, src);
-        src += rstep;
-      }
-    }
+// Low-res corners (u, u+1, u+2) x (v, v+1) of a thread's block pair, edge clamped; u and cols are even.
+template <int NCH>
+__device__ __forceinline__ void inv4_corners(const uint8_t *__restrict__ R, int item, const Geom &g, int v, int u,
+                                             uint32_t (&top)[NCH], uint32_t (&bot)[NCH]) {
+  const int v2 = min(v + 1, g.rows - 1), u2 = min(u + 2, g.cols - 1);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint8_t *Rc = R + ((size_t)item * NCH + c) * g.rows * g.cols;
+    const uint8_t *r0 = Rc + (size_t)v * g.cols, *r1 = Rc + (size_t)v2 * g.cols;
+    top[c] = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(r0 + u)) | ((uint32_t)__ldg(r0 + u2) << 16);
+    bot[c] = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(r1 + u)) | ((uint32_t)__ldg(r1 + u2) << 16);
   }
-  const int pre = T->pre, tab_bias = T->bias;
-  const bool overflow = T->overflow != 0;
-#ifdef HIMG_FORCE_PRE3  // (instruction counting only: tools/phase_count.py)
+}
+
+// The inverse proper for ONE thread = one block pair: codes in the thread's two byte columns `col` of a
+// shared-memory tile whose rows
+// (scan positions, channel-major) are PITCH bytes apart; the image's tables in sDq / sTab; pixels to
+// dst0 (row 0 of the pair) + y * row_bytes.  No barrier inside.
+template <int NCH, int PITCH>
+__device__ __forceinline__ void inv4_compute(uint8_t *col, const uint8_t *sDq, const uint32_t *sTab, int pre, int tab_bias,
+                                             bool overflow, bool ycbcr, bool active, const uint32_t (&top)[NCH],
+                                             const uint32_t (&bot)[NCH], uint8_t *dst0, size_t row_bytes, uint32_t one) {
+#ifdef HIMG_FORCE_PRE3  // (instruction counting only)
   const bool pre3 = true;
 #else
   const bool pre3 = pre == 3;
 #endif
   const uint32_t wide_mask = pre3 ? 0xfc00fc00u : 0xe000e000u;  // a lane outside the table's narrow range
-  const bool ycbcr = T->ycbcr != 0;
-  const bool active = t < nact;
-  int v, p;
-  locate(active ? t : 0, v, p);
-  const int u = 2 * p;
-  // low-res corners (u, u+1, u+2) x (v, v+1), edge clamped; u and cols are even
-  uint32_t top[NCH], bot[NCH];
-  {
-    const int v2 = min(v + 1, g.rows - 1), u2 = min(u + 2, g.cols - 1);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const uint8_t *Rc = R + ((size_t)blockIdx.z * NCH + c) * g.rows * g.cols;
-      const uint8_t *r0 = Rc + (size_t)v * g.cols, *r1 = Rc + (size_t)v2 * g.cols;
-      top[c] = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(r0 + u)) | ((uint32_t)__ldg(r0 + u2) << 16);
-      bot[c] = (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(r1 + u)) | ((uint32_t)__ldg(r1 + u2) << 16);
-    }
-  }
-  uint8_t *col = sPl + 2 * t;  // this thread's two byte columns of the tile
   const uint32_t dq_base = smem_u32(sDq);  // (table offsets -> shared-memory addresses: added at the lookups' base)
-  cp_async_wait_all();
-  __syncthreads();  // the only barrier: from here on a thread touches its own two byte columns only
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     uint8_t *cc = col + c * 64 * PITCH;
@@ -425,7 +362,7 @@ __global__ void __launch_bounds__(TP, 2)
         wb[m] = __byte_perm(pq, q, 0x7632);
       }
       if (active) {
-        uint4 *dst = reinterpret_cast<uint4 *>(img + ((size_t)(8 * v + y) * g.w + (size_t)u * 8) * NCH);
+        uint4 *dst = reinterpret_cast<uint4 *>(dst0 + (size_t)y * row_bytes);
         if (NCH == 1) {
           dst[0] = make_uint4(wa[0], wa[1], wb[0], wb[1]);
         } else {
@@ -436,6 +373,84 @@ __global__ void __launch_bounds__(TP, 2)
       }
     }
   }
+}
+
+// grid (ceil(rows * cols / 2 / TP), 1, n), block TP: one tile of TP consecutive block pairs per CTA.
+// dynamic smem: tile [NCH * 64][2 * TP] | dq tables [8][256] u16 | table offsets [2][64] u32
+//
+// The codes of the tile and the image's tables arrive by cp.async (the threads of a tile row copy 2 * TP
+// contiguous bytes), the CTA meets at one barrier, then the warps run the three channels and the
+// output phase WITHOUT further barriers: a thread only ever touches its own two byte columns of the tile,
+// and the phases of the inverse load different pipes (LSU in the gather, FMA in the butterflies, ALU in
+// the clamps), so warps that drift apart fill each other's gaps.
+// (Measured and dropped: several tiles per CTA with the next tile prefetched into L2 or copied early from
+// inside the output phase, and tiles owned by single warps -- all slower than fresh CTAs whose start-up
+// overlaps the other resident CTA.)
+template <int NCH, int TP>
+__global__ void __launch_bounds__(TP, 2)
+    k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
+               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels, uint32_t one) {
+  extern __shared__ __align__(128) uint8_t sPl[];
+  constexpr int PITCH = 2 * TP, CPR = TP / 8;  // bytes per tile row, 16-byte chunks per tile row
+  static_assert(TP % 32 == 0 && TP == 8 * CPR, "a CTA is 8 groups of one thread per chunk of a tile row");
+  uint8_t *sDq = sPl + NCH * 64 * PITCH;
+  uint32_t *sTab = reinterpret_cast<uint32_t *>(sDq + kInvSlots * 256 * 2);
+
+  const int t = threadIdx.x;
+  const int PR = g.cols >> 1, total = g.rows * PR;
+  const int f0 = blockIdx.x * TP;
+  const int nact = min(TP, total - f0);
+  const uint8_t *ipl = planes + (size_t)blockIdx.z * g.planes_bytes;
+  uint8_t *img = pixels + (size_t)blockIdx.z * g.out_img_bytes;
+  const InvTables *T = reinterpret_cast<const InvTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tab_stride);
+  // block row / first pair of the tile's first element: one division per CTA, everything else by
+  // carrying (a tile spans few block rows unless the image is very narrow)
+  const int v0 = f0 / PR, p0 = f0 - v0 * PR;
+  auto locate = [&](int k, int &v, int &p) {  // element f0 + k of the image -> block row, pair in the row
+    if (PR >= 32) {
+      v = v0;
+      p = p0 + k;
+      while (p >= PR) {
+        p -= PR;
+        ++v;
+      }
+    } else {
+      v = (f0 + k) / PR;
+      p = f0 + k - v * PR;
+    }
+  };
+  {
+    // the image's tables, then the tile: thread -> 16-byte chunk t % CPR (8 pairs of ONE block row:
+    // cols % 16 == 0) of the tile rows t / CPR + 8 i; the threads of a row copy 2 * TP contiguous bytes
+    const uint4 *tsrc = reinterpret_cast<const uint4 *>(T);
+    for (int i = t; i < kInvTableBytes / 16; i += TP) cp_async16(sDq + 16 * i, tsrc + i);
+    const int cq = t % CPR, r0 = t / CPR;
+    if (8 * cq < nact) {
+      int vl, pl;
+      locate(8 * cq, vl, pl);
+      const uint8_t *src = ipl + (size_t)vl * g.seg + 2 * pl + (size_t)r0 * g.cols;
+      uint8_t *dst = sPl + r0 * PITCH + cq * 16;
+      const size_t rstep = (size_t)8 * g.cols;
+#pragma unroll 8
+      for (int i = 0; i < NCH * 8; ++i) {
+        cp_async16(dst + i * 8 * PITCH, src);
+        src += rstep;
+      }
+    }
+  }
+  const int pre = T->pre, tab_bias = T->bias;
+  const bool overflow = T->overflow != 0;
+  const bool ycbcr = T->ycbcr != 0;
+  const bool active = t < nact;
+  int v, p;
+  locate(active ? t : 0, v, p);
+  const int u = 2 * p;
+  uint32_t top[NCH], bot[NCH];
+  inv4_corners<NCH>(R, blockIdx.z, g, v, u, top, bot);
+  cp_async_wait_all();
+  __syncthreads();  // the only barrier: from here on a thread touches its own two byte columns only
+  inv4_compute<NCH, PITCH>(sPl + 2 * t, sDq, sTab, pre, tab_bias, overflow, ycbcr, active, top, bot,
+                           img + ((size_t)(8 * v) * g.w + (size_t)u * 8) * NCH, (size_t)g.w * NCH, one);
 }
 
 }  // namespace himgcu
