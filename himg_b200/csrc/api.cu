@@ -20,6 +20,7 @@
 #include "tables.h"
 #include "xform_fwd3.cuh"
 #include "xform_inv2.cuh"
+#include "xform_avg2.cuh"
 #include "xform_inv4.cuh"
 #include "xform_kernels.cuh"
 
@@ -329,11 +330,33 @@ int launch_avg(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, b
   return HIMGCU_OK;
 }
 
+void make_colour(int nch, bool ycbcr, ColourW *cw);
+
+template <int NCH>
+int launch_avg2(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, bool ycbcr, uint8_t *d_avg) {
+  Avg2Params P;
+  make_colour(g.nch, ycbcr, P.cw);
+  dim3 grid((g.cols / 2 + kAvg2Threads - 1) / kAvg2Threads, g.rows, n);
+  LAUNCH("k_lowres_avg", (k_lowres_avg2<NCH>), grid, kAvg2Threads, 0, d_pixels, g, P, d_avg);
+  return HIMGCU_OK;
+}
+
 int stage_lowres(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, bool ycbcr, uint8_t *d_L) {
   uint8_t *d_avg;
   const size_t nlow = (size_t)n * g.nch * g.rows * g.cols;
   ENSURE("avg", nlow, d_avg);
   int rc;
+  // lane-pair fast path: whole 16-pixel block pairs, tightly packed pixels, 16-byte aligned rows
+  const bool fast = !ctx->force_generic && !(ctx->xform_variant & 1) && g.pstride == g.nch && (g.w % 16) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d_pixels) & 15) == 0 && (g.img_bytes & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d_avg) & 1) == 0 && (g.nch == 1 || g.nch == 3 || g.nch == 4);
+  if (fast) {
+    switch (g.nch) {
+      case 1: rc = launch_avg2<1>(ctx, d_pixels, n, g, false, d_avg); break;
+      case 3: rc = launch_avg2<3>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
+      default: rc = launch_avg2<4>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
+    }
+  } else
   switch (g.nch) {
     case 1: rc = launch_avg<1>(ctx, d_pixels, n, g, false, d_avg); break;
     case 2: rc = launch_avg<2>(ctx, d_pixels, n, g, false, d_avg); break;
