@@ -364,9 +364,9 @@ int stage_lowres(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g,
     default: rc = launch_avg<4>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
   }
   if (rc) return rc;
-  const int threads = 256;
-  const unsigned blocks = (unsigned)((nlow + threads - 1) / threads);
-  LAUNCH("k_lowres_comp", k_lowres_comp, blocks, threads, 0, d_avg, n * g.nch, g.rows, g.cols, d_L);
+  const int threads = std::min(256, (g.cols + 31) & ~31);
+  LAUNCH("k_lowres_comp", k_lowres_comp, dim3((unsigned)(n * g.nch), (g.rows + kCompRows - 1) / kCompRows), threads, 0, d_avg,
+         n * g.nch, g.rows, g.cols, d_L);
   return HIMGCU_OK;
 }
 

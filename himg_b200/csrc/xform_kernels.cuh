@@ -137,19 +137,32 @@ __global__ void __launch_bounds__(kTile) k_lowres_avg(const uint8_t *__restrict_
   }
 }
 
-// 1/16-pixel phase compensation (downsampled.cpp:96-113).  One thread per low-res sample.
+// 1/16-pixel phase compensation (downsampled.cpp:96-113): L = blend(blend(row v-1), blend(row v)) with
+// blend(row r) = (a[r][u-1] + 15 a[r][u] + 8) >> 4, edges clamped.  A thread owns column u of
+// kCompRows consecutive rows and computes every row blend once (the lower blend of row v is the upper
+// blend of row v+1); 32-bit indices only (a 64-bit division per sample was most of the first version).
+// grid (planes, ceil(rows / kCompRows)), any block size (threads stride over the columns).
+constexpr int kCompRows = 4;
 __global__ void k_lowres_comp(const uint8_t *__restrict__ avg, int planes, int rows, int cols,
                               uint8_t *__restrict__ L) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t per = (size_t)rows * cols;
-  if (idx >= per * planes) return;
-  const size_t pl = idx / per;
-  const int rem = (int)(idx - pl * per), v = rem / cols, u = rem - v * cols;
-  const uint8_t *a = avg + pl * per;
-  const int vp = max(v - 1, 0), up = max(u - 1, 0);
-  const int a1 = (a[vp * cols + up] + 15 * a[vp * cols + u] + 8) >> 4;
-  const int a2 = (a[v * cols + up] + 15 * a[v * cols + u] + 8) >> 4;
-  L[idx] = (uint8_t)((a1 + 15 * a2 + 8) >> 4);
+  const size_t base = (size_t)blockIdx.x * rows * cols;
+  const uint8_t *a = avg + base;
+  uint8_t *o = L + base;
+  const int v0 = blockIdx.y * kCompRows;
+  for (int u = threadIdx.x; u < cols; u += blockDim.x) {
+    const int up = max(u - 1, 0);
+    const int rp = max(v0 - 1, 0);
+    int prev = (a[rp * cols + up] + 15 * a[rp * cols + u] + 8) >> 4;
+#pragma unroll
+    for (int k = 0; k < kCompRows; ++k) {
+      const int v = v0 + k;
+      if (v < rows) {
+        const int cur = (a[v * cols + up] + 15 * a[v * cols + u] + 8) >> 4;
+        o[v * cols + u] = (uint8_t)((prev + 15 * cur + 8) >> 4);
+        prev = cur;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
