@@ -758,8 +758,8 @@ int launch_stream_cluster(himgcu_ctx *ctx, const char *name, int n, const uint8_
   cudaError_t e;
   {
     LaunchScope ls_(ctx, name);
-    e = cudaLaunchKernelEx(&cfg, k_dec_stream_par<false, kDecCluster>, d_in, d_cd, d_tree, d_seg, 1, out_seg, d_out, out_stride,
-                           d_status);
+    e = cudaLaunchKernelEx(&cfg, k_dec_stream_par<false, kDecCluster>, d_in, d_cd, d_tree, const_cast<SegRef *>(d_seg), 1, out_seg,
+                           d_out, out_stride, d_status, 0, 0);
   }
   if (e != cudaSuccess) return fail(ctx, HIMGCU_ERR_CUDA, "launch %s failed: %s", name, cudaGetErrorString(e));
   *launched = true;
@@ -834,10 +834,20 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
     if (rc_l) CK(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
   }
   if (rc_l) return rc_l;
-  LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
-         d_status);
   // a warp per block row when the batch alone fills the GPU, wider teams for few streams
   const int fres_team = decode_team((long long)n * g.rows, g.seg, kParFresThreads);
+  // Few streams (single images): the serial walk over the segment headers runs inside the decode kernel
+  // and the rows decode as soon as their entry is published (all CTAs of such a grid are resident at once)
+  const bool inline_walk = fres_team > 32 && !ctx->force_generic && (long long)n * (g.rows + 1) * fres_team <= 148LL * 2048;
+  if (inline_walk) {
+    CK(cudaMemsetAsync(d_fseg, 0xfe, (size_t)n * g.rows * sizeof(SegRef), ctx->stream));  // kSegNotReady
+    LAUNCH("k_dec_stream_fres", k_dec_stream_par<false>, dim3(g.rows + 1, n), fres_team, 0, d_himg, d_fcd, d_ftree, d_fseg,
+           g.rows, g.seg, d_planes, g.planes_bytes, d_status, 1, lenient);
+    if (fork) CK(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));
+    return stage_inverse(ctx, d_planes, d_R, n, g, d_tabs, sizeof(DecTables), d_pixels);
+  }
+  LAUNCH("k_dec_segtab", k_dec_segtab, nb, 128, 0, d_himg, d_fcd, d_ftree, n, g.rows, g.seg, 1, lenient, d_fseg,
+         d_status);
   if (fres_team == 32) {
     LAUNCH("k_dec_stream_fres", k_dec_stream_par<true>, dim3((g.rows + kParWarpTeams - 1) / kParWarpTeams, n),
            32 * kParWarpTeams, 0, d_himg, d_fcd, d_ftree, d_fseg, g.rows, g.seg, d_planes, g.planes_bytes, d_status);

@@ -77,7 +77,7 @@ struct __align__(16) DecTree {
   int single;    // single-leaf tree
 };
 
-struct SegRef {
+struct alignas(8) SegRef {
   uint32_t off;   // relative to the chunk payload
   uint32_t size;  // 0xffffffff = invalid
 };
@@ -381,68 +381,91 @@ __global__ void __launch_bounds__(kDecTreeThreads)
 // ---- segment table (huffman_dec.cpp:215-251) ---------------------------------------------------
 // One thread per chunk.  mode: 0 = unframed chunk decoded as ONE stream (LRES, Uncompress);
 // 1 = framed chunk of nseg block rows (FRES, UncompressBlock).
-__global__ void k_dec_segtab(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
-                             const DecTree *__restrict__ trees, int n, int nseg, int seg_size, int mode,
-                             int lenient, SegRef *__restrict__ segs, int *__restrict__ status) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  SegRef *S = segs + (size_t)i * nseg;
-  for (int b = 0; b < nseg; ++b) S[b].size = 0xffffffffu, S[b].off = 0;
-  const ChunkDesc d = cd[i];
-  const DecTree *T = trees + i;
-  if (!d.ok || !T->ok) {
-    atomicMax(&status[i], 1);
-    return;
+//
+// The headers form a chain (each one sits behind the previous payload): ~0.3 us per segment, 100-350 us
+// for the 270-1024 block rows of a single 4K / 8K image.  With PUBLISH the walk runs INSIDE the stream
+// decode kernel (its first CTA) and releases every entry as soon as it is known; the decoding CTAs
+// acquire theirs, so the decode of the first rows overlaps the rest of the walk.  Entries start as
+// kSegNotReady (host memset) and always end up valid or invalid (0xffffffff).
+constexpr uint32_t kSegNotReady = 0xfefefefeu;
+
+// An entry is ONE aligned 8-byte word (offset | size << 32): a single store publishes it and a single
+// load takes it, no fence (a release store per entry tripled the time of the walk).
+static_assert(sizeof(SegRef) == 8, "SegRef is published as one 64-bit word");
+template <bool PUBLISH>
+__device__ __forceinline__ void seg_store(SegRef *s, uint32_t off, uint32_t size) {
+  if (PUBLISH) {
+    *reinterpret_cast<volatile unsigned long long *>(s) = (unsigned long long)off | ((unsigned long long)size << 32);
+  } else {
+    s->off = off;
+    s->size = size;
   }
+}
+__device__ __forceinline__ SegRef seg_acquire(const SegRef *s) {
+  SegRef r;
+  for (;;) {
+    const unsigned long long v = *reinterpret_cast<const volatile unsigned long long *>(s);
+    r.off = (uint32_t)v;
+    r.size = (uint32_t)(v >> 32);
+    if (r.size != kSegNotReady) break;
+    __nanosleep(500);
+  }
+  return r;
+}
+
+template <bool PUBLISH>
+__device__ void segtab_walk(const uint8_t *__restrict__ data, const ChunkDesc d, const DecTree *__restrict__ T, int nseg,
+                            int seg_size, int mode, int lenient, SegRef *__restrict__ S, int *__restrict__ status_i) {
+  int done = 0;  // entries stored so far; on every exit the remaining ones become invalid
+  auto fail = [&]() {
+    for (int b = done; b < nseg; ++b) seg_store<PUBLISH>(S + b, 0, 0xffffffffu);
+    atomicMax(status_i, 1);
+  };
+  if (!d.ok || !T->ok) return fail();
   const uint32_t start = (uint32_t)T->data_off;
   if (mode == 0) {
     // HuffmanDec(in, size, 0): block size = packed size => never framed; an empty payload can
     // only produce an empty output (huffman_dec.cpp:278-279).
-    if (start >= d.size) {
-      atomicMax(&status[i], 1);
-      return;
-    }
-    S[0].off = start;
-    S[0].size = d.size - start;
+    if (start >= d.size) return fail();
+    seg_store<PUBLISH>(S, start, d.size - start);
+    done = 1;
+    for (int b = done; b < nseg; ++b) seg_store<PUBLISH>(S + b, 0, 0xffffffffu);
     return;
   }
   // The reference decides framing by comparing the UNPACKED block size with the PACKED chunk size
   // (huffman_dec.cpp:217-218); the encoder framed iff there is more than one segment.
   const bool framed = lenient ? (nseg > 1) : ((uint32_t)seg_size < d.size);
   if (!framed) {
-    if (!lenient || start >= d.size) {  // UncompressBlock refuses unframed data (:265)
-      atomicMax(&status[i], 1);
-      return;
-    }
-    S[0].off = start;
-    S[0].size = d.size - start;
+    if (!lenient || start >= d.size) return fail();  // UncompressBlock refuses unframed data (:265)
+    seg_store<PUBLISH>(S, start, d.size - start);
+    done = 1;
+    for (int b = done; b < nseg; ++b) seg_store<PUBLISH>(S + b, 0, 0xffffffffu);
     return;
   }
   const uint8_t *p = data + d.off;
   uint32_t pos = start;
   for (int b = 0; b < nseg; ++b) {
-    if (pos + 2 > d.size) {
-      atomicMax(&status[i], 1);
-      return;
-    }
+    if (pos + 2 > d.size) return fail();
     uint32_t sz = (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8);
     pos += 2;
     if (sz & 0x8000u) {
-      if (pos + 2 > d.size) {
-        atomicMax(&status[i], 1);
-        return;
-      }
+      if (pos + 2 > d.size) return fail();
       sz = (sz & 0x7fffu) | (((uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8)) << 15);
       pos += 2;
     }
-    if ((unsigned long long)pos + sz > d.size) {
-      atomicMax(&status[i], 1);
-      return;
-    }
-    S[b].off = pos;
-    S[b].size = sz;
+    if ((unsigned long long)pos + sz > d.size || sz == kSegNotReady) return fail();
+    seg_store<PUBLISH>(S + b, pos, sz);
+    done = b + 1;
     pos += sz;
   }
+}
+
+__global__ void k_dec_segtab(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
+                             const DecTree *__restrict__ trees, int n, int nseg, int seg_size, int mode,
+                             int lenient, SegRef *__restrict__ segs, int *__restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  segtab_walk<false>(data, cd[i], trees + i, nseg, seg_size, mode, lenient, segs + (size_t)i * nseg, status + i);
 }
 
 // ---- subsequence-parallel stream decode ---------------------------------------------------------
@@ -563,9 +586,9 @@ constexpr int kParWarpTeams = 8;  // WARP_TEAMS: streams (one warp each) per CTA
 //   and one CTA (one SM) was the whole machine for it.
 template <bool WARP_TEAMS, int CL = 1>
 __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDesc *__restrict__ cd,
-                                 const DecTree *__restrict__ trees, const SegRef *__restrict__ segs, int nseg,
+                                 const DecTree *__restrict__ trees, SegRef *__restrict__ segs, int nseg,
                                  int out_seg, uint8_t *__restrict__ out, unsigned long long out_stride,
-                                 int *__restrict__ status) {
+                                 int *__restrict__ status, int inline_walk = 0, int lenient = 0) {
   __shared__ __align__(16) uint2 lut2[kLutSize];  // the single-token LUT stays in global memory (rare path)
   __shared__ uint32_t s_nodes[kMaxNodes + 1];
   __shared__ uint32_t s_sub[kSubCap << kSubBits];
@@ -579,11 +602,19 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   static_assert(!(WARP_TEAMS && CL > 1), "clusters are for the one-stream-per-team variant");
   namespace cg = cooperative_groups;
   const int item = blockIdx.y;
+  // inline_walk (one CTA per stream only): CTA 0 of every item walks the segment headers of the framed
+  // chunk and publishes the table (see segtab_walk); the stream of CTA x is segment x - 1
+  if (!WARP_TEAMS && CL == 1 && inline_walk && blockIdx.x == 0) {
+    if (threadIdx.x == 0)
+      segtab_walk<true>(data, cd[item], trees + item, nseg, out_seg, 1, lenient, segs + (size_t)item * nseg, status + item);
+    return;
+  }
   const int rank = CL > 1 ? (int)cg::this_cluster().block_rank() : 0;
   const int tm = WARP_TEAMS ? (int)(threadIdx.x >> 5) : 0;  // team inside the CTA
   const int lt = WARP_TEAMS ? (int)(threadIdx.x & 31) : (int)threadIdx.x;  // index inside this CTA's share of the team
   const int t = lt + rank * (int)blockDim.x, team = WARP_TEAMS ? 32 : CL * (int)blockDim.x;
-  const int b = WARP_TEAMS ? (int)blockIdx.x * kParWarpTeams + tm : (int)blockIdx.x / CL;
+  const int b = WARP_TEAMS ? (int)blockIdx.x * kParWarpTeams + tm
+                           : (CL == 1 && inline_walk ? (int)blockIdx.x - 1 : (int)blockIdx.x / CL);
   auto tsync = [] {
     if (WARP_TEAMS) __syncwarp();
     else if (CL > 1) cg::this_cluster().sync();
@@ -611,7 +642,16 @@ __global__ void k_dec_stream_par(const uint8_t *__restrict__ data, const ChunkDe
   }
   __syncthreads();
   if (WARP_TEAMS && b >= nseg) return;
-  const SegRef sr = segs[(size_t)item * nseg + b];
+  SegRef sr;
+  if (!WARP_TEAMS && CL == 1 && inline_walk) {
+    // ONE thread polls (a whole grid of polling threads slowed the walker's own dependent loads down)
+    __shared__ SegRef s_sr;
+    if (threadIdx.x == 0) s_sr = seg_acquire(segs + (size_t)item * nseg + b);
+    __syncthreads();
+    sr = s_sr;
+  } else {
+    sr = segs[(size_t)item * nseg + b];
+  }
   if (!T->ok || sr.size == 0xffffffffu || sr.size == 0) {  // an empty stream cannot produce out_seg > 0 bytes
     if (t == 0) atomicMax(&status[item], 1);
     return;
