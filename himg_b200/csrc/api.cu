@@ -581,7 +581,7 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
   size_t prefix_off = 0;
   TreeOut *d_trees[2];
   uint32_t *d_seghist[2], *d_bits[2], *d_pos[2];
-  uint32_t *d_part[2];
+  uint32_t *d_part[2], *d_pbits[2];
   TreeParams TP;
   memset(&TP, 0, sizeof(TP));
   ItemLists lists[2];
@@ -619,12 +619,20 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
       ENSURE((tag + "_itcnt").c_str(), slots * sizeof(uint32_t), il.count);
       il.pieces_per_part = ppp;
     }
+    ENSURE((tag + "_partbits").c_str(), (size_t)n * hg.nseg * hg.nsub * sizeof(uint32_t), d_pbits[k]);
+    uint32_t *d_total = nullptr;
+    if (!ctx->force_generic) {  // chunk histograms summed by the histogram kernel itself
+      ENSURE((tag + "_histtotal").c_str(), (size_t)n * kSyms * sizeof(uint32_t), d_total);
+      CK(cudaMemsetAsync(d_total, 0, (size_t)n * kSyms * sizeof(uint32_t), ctx->stream));
+    }
     if (ctx->force_generic) LAUNCH("k_huff_hist", k_huff_hist, grid, kHuffThreads, 0, chunks[k].d_in, hg, d_seghist[k]);
-    else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k], il);
+    else LAUNCH("k_huff_hist", k_huff_hist2, grid, kTokThreads, 0, chunks[k].d_in, hg, d_seghist[k], il, d_total);
+    TP.total[k] = d_total;
     TP.seghist[k] = d_seghist[k];
     TP.trees[k] = d_trees[k];
     TP.rows[k] = hg.nseg * hg.nsub;
     LayoutChunk &C = P.ch[k];
+    C.part_bits = d_pbits[k];
     C.seghist = d_seghist[k];
     C.trees = d_trees[k];
     C.seg_bits = d_bits[k];
@@ -639,6 +647,10 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
     prefix_off += chunks[k].prefix.size();
   }
   LAUNCH("k_huff_tree", k_huff_tree, dim3(n, nchunks), kTreeThreads, 0, TP, d_err);
+  for (int k = 0; k < nchunks; ++k) {
+    const int rows = chunks[k].hg.nseg * chunks[k].hg.nsub;
+    LAUNCH("k_huff_layout", k_huff_segbits, dim3((rows + 7) / 8, n), 256, 0, d_seghist[k], d_trees[k], rows, d_pbits[k]);
+  }
   LAUNCH("k_huff_layout", k_huff_layout, n, kLayoutThreads, 0, P);
   const size_t win_bytes = (kWinWords + 2) * sizeof(uint32_t);
   if (ctx->force_generic)  // static + dynamic shared memory of the first-generation packer exceed 48 KiB

@@ -319,7 +319,8 @@ __device__ __forceinline__ size_t item_slot(const ItemLists &L, const HuffGeom &
 
 // grid (nseg * nsub, n), block kTokThreads.  seghist: [n][nseg * nsub][261].
 __global__ void __launch_bounds__(kTokThreads, 8)
-    k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist, ItemLists lists) {
+    k_huff_hist2(const uint8_t *__restrict__ in, HuffGeom hg, uint32_t *__restrict__ seghist, ItemLists lists,
+                 uint32_t *__restrict__ total) {
   __shared__ uint32_t sh[kSyms];
   __shared__ uint32_t ws[kTokWarps + 1];
   __shared__ uint32_t rows[kTokThreads * kRowWords];
@@ -364,7 +365,13 @@ __global__ void __launch_bounds__(kTokThreads, 8)
   }
   __syncthreads();
   uint32_t *dst = seghist + ((size_t)blockIdx.y * hg.nseg * hg.nsub + blockIdx.x) * kSyms;
-  for (int i = threadIdx.x; i < kSyms; i += blockDim.x) dst[i] = sh[i];
+  for (int i = threadIdx.x; i < kSyms; i += blockDim.x) {
+    const uint32_t v = sh[i];
+    dst[i] = v;
+    // the chunk's histogram (what the tree is built from): summed here, so that k_huff_tree does not
+    // walk over the rows -- a chain of dependent L2 round trips, the longest part of it for tall images
+    if (total && v) atomicAdd(&total[(size_t)blockIdx.y * kSyms + i], v);
+  }
 }
 
 // ---- K-tree ----------------------------------------------------------------------------------
@@ -373,6 +380,7 @@ constexpr int kTreeThreads = 288;
 // The (up to two) chunks of an image get their trees in ONE launch: the construction is a serial
 // chain of ~80 us per tree, and two CTAs run it side by side.
 struct TreeParams {
+  const uint32_t *total[2];    // [n][261] chunk histograms summed by k_huff_hist2, or null: sum the rows here
   const uint32_t *seghist[2];  // [n][rows][261]
   TreeOut *trees[2];           // [n]
   int rows[2];                 // histogram rows per item (segments x parts)
@@ -402,18 +410,21 @@ __global__ void __launch_bounds__(kTreeThreads)
   // 1. chunk histogram = sum of its segments' histograms (coalesced across threads)
   uint32_t my = 0;
   if (t < kSyms) {
-    // independent loads, eight in flight: one dependent L2 round trip per segment made this loop the
-    // longest part of the kernel for tall images
-    const uint32_t *p = seghist + (size_t)blockIdx.x * nseg * kSyms + t;
-    int s = 0;
-    for (; s + 8 <= nseg; s += 8) {
-      uint32_t v[8];
+    if (P.total[blockIdx.y]) {
+      my = P.total[blockIdx.y][(size_t)blockIdx.x * kSyms + t];
+    } else {
+      // independent loads, eight in flight
+      const uint32_t *p = seghist + (size_t)blockIdx.x * nseg * kSyms + t;
+      int s = 0;
+      for (; s + 8 <= nseg; s += 8) {
+        uint32_t v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (size_t)(s + k) * kSyms);
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(p + (size_t)(s + k) * kSyms);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) my += v[k];
+        for (int k = 0; k < 8; ++k) my += v[k];
+      }
+      for (; s < nseg; ++s) my += __ldg(p + (size_t)s * kSyms);
     }
-    for (; s < nseg; ++s) my += __ldg(p + (size_t)s * kSyms);
     out->hist[t] = my;
     s_code[t] = 0;
     s_len[t] = 0;
@@ -539,6 +550,7 @@ __global__ void __launch_bounds__(kTreeThreads)
 
 // ---- K-layout --------------------------------------------------------------------------------
 struct LayoutChunk {
+  const uint32_t *part_bits;  // [n][nseg][nsub] bits of every part (k_huff_segbits)
   const uint32_t *seghist;  // [n][nseg][261]
   const TreeOut *trees;     // [n]
   uint32_t *seg_bits;       // [n][nseg] out
@@ -563,6 +575,26 @@ struct LayoutParams {
 
 constexpr int kLayoutThreads = 256;
 
+// Bits of every part of every segment = its histogram . (code length + extra bits): a warp per histogram row.
+// (One CTA per image used to do this inside k_huff_layout: 100 us for the 1024 rows of a single 8K image.)
+// grid (ceil(rows / 8), n), block 256.
+__global__ void __launch_bounds__(256) k_huff_segbits(const uint32_t *__restrict__ seghist, const TreeOut *__restrict__ trees,
+                                                      int rows, uint32_t *__restrict__ part_bits) {
+  const int item = blockIdx.y, lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TreeOut *tr = trees + item;
+  const uint32_t *h = seghist + ((size_t)item * rows + row) * kSyms;
+  unsigned long long pb = 0;
+#pragma unroll
+  for (int k = 0; k < (kSyms + 31) / 32; ++k) {
+    const int s = lane + 32 * k;
+    if (s < kSyms) pb += (unsigned long long)__ldg(h + s) * (uint32_t)(tr->len[s] + sym_extra_bits(s));
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) pb += __shfl_xor_sync(0xffffffffu, pb, d);
+  if (lane == 0) part_bits[(size_t)item * rows + row] = (uint32_t)pb;
+}
+
 __device__ __forceinline__ void put_u32le(uint8_t *p, uint32_t x) {
   p[0] = (uint8_t)x;
   p[1] = (uint8_t)(x >> 8);
@@ -572,11 +604,10 @@ __device__ __forceinline__ void put_u32le(uint8_t *p, uint32_t x) {
 
 // grid (n).
 __global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_constant__ LayoutParams P) {
-  __shared__ uint32_t s_lenx[kSyms];
   __shared__ uint32_t ws[kLayoutThreads / 32 + 1];
   __shared__ unsigned long long s_chunk_bytes[2];
   __shared__ int s_too_long;
-  const int item = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int item = blockIdx.x, t = threadIdx.x, lane = t & 31;
   uint8_t *out = P.out + (size_t)item * P.out_stride;
   if (t == 0) s_too_long = 0;
 
@@ -585,30 +616,24 @@ __global__ void __launch_bounds__(kLayoutThreads) k_huff_layout(const __grid_con
     const LayoutChunk &C = P.ch[k];
     const TreeOut *tr = C.trees + item;
     __syncthreads();
-    for (int s = t; s < kSyms; s += blockDim.x) {
-      s_lenx[s] = (uint32_t)tr->len[s] + sym_extra_bits(s);
+    for (int s = t; s < kSyms; s += blockDim.x)
       if (tr->len[s] > 32) s_too_long = 1;  // the reference's codes are uint32_t (huffman_enc.cpp:179): unsupported
-    }
     if (t == 0) s_chunk_bytes[k] = 0;
     __syncthreads();
     unsigned long long mine = 0;
-    for (int b = wid; b < C.nseg; b += kLayoutThreads / 32) {
+    for (int b = t; b < C.nseg; b += kLayoutThreads) {  // a thread per segment: running sum over its parts
       unsigned long long bits = 0;
       for (int part = 0; part < C.nsub; ++part) {
-        const uint32_t *h = C.seghist + (((size_t)item * C.nseg + b) * C.nsub + part) * kSyms;
-        unsigned long long pb = 0;
-        for (int s = lane; s < kSyms; s += 32) pb += (unsigned long long)h[s] * s_lenx[s];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) pb += __shfl_xor_sync(0xffffffffu, pb, d);
-        if (lane == 0) C.part_start[((size_t)item * C.nseg + b) * C.nsub + part] = (uint32_t)bits;
-        bits += pb;
+        const size_t pi = ((size_t)item * C.nseg + b) * C.nsub + part;
+        C.part_start[pi] = (uint32_t)bits;
+        bits += C.part_bits[pi];
       }
-      if (lane == 0) {
-        C.seg_bits[(size_t)item * C.nseg + b] = (uint32_t)bits;
-        const unsigned long long sz = (bits + 7) >> 3;
-        mine += sz + (C.framed ? (sz <= 0x7fff ? 2 : 4) : 0);
-      }
+      C.seg_bits[(size_t)item * C.nseg + b] = (uint32_t)bits;
+      const unsigned long long sz = (bits + 7) >> 3;
+      mine += sz + (C.framed ? (sz <= 0x7fff ? 2 : 4) : 0);
     }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
     if (lane == 0 && mine) atomicAdd(&s_chunk_bytes[k], mine);
   }
   __syncthreads();
