@@ -60,6 +60,10 @@ SHAPES = [(64, 48, 3), (40, 24, 1), (37, 21, 1), (96, 64, 4), (500, 300, 3), (51
           (1032, 40, 3), (2056, 16, 1), (136, 264, 2), (264, 136, 4)]
 
 
+FLAT_SHAPES = [(1920, 64, 3), (272, 200, 3), (16, 4104, 1), (4112, 16, 3), (3840, 24, 3), (1040, 72, 1), (304, 136, 4),
+               (32, 2072, 3)]
+
+
 # ---------------------------------------------------------------------------------------------
 # stages, encode side
 # ---------------------------------------------------------------------------------------------
@@ -73,6 +77,20 @@ def test_stage_lowres(ctx, port, shape, ycbcr):
     want = port.lowres_sample(cm)
     got = ctx.stage_lowres(dev(img[None]), yc).cpu().numpy()[0]
     assert_same(got, want, f"lowres {shape} ycbcr={yc}")
+
+
+def test_stage_lowres_lane_pair_path(ctx, port):
+    # width % 16 == 0: k_lowres_avg2 (block pairs, dp4a colour map) for 1, 3 and 4 channels, more than
+    # one CTA per window row (4112 / 16 > 128 pairs), single block rows and clipped top / bottom windows
+    for (w, h, n) in FLAT_SHAPES + [(16, 8, 3), (48, 13, 1)]:
+        for ycbcr in (True, False):
+            img = port.synth(w, h, n, 11, 40)
+            yc = ycbcr and n >= 3
+            cm = port.rgb_to_ycbcr(img) if yc else img
+            got = ctx.stage_lowres(dev(np.stack([img, img[:, ::-1].copy()])), yc).cpu().numpy()
+            assert_same(got[0], port.lowres_sample(cm), f"lowres {(w, h, n)} ycbcr={yc}")
+            cm1 = port.rgb_to_ycbcr(img[:, ::-1].copy()) if yc else img[:, ::-1].copy()
+            assert_same(got[1], port.lowres_sample(cm1), f"lowres, second image {(w, h, n)}")
 
 
 def test_stage_lowres_batch_and_stride(ctx, port):
@@ -115,8 +133,6 @@ def test_stage_forward(ctx, port, shape, quality, ycbcr):
 # Flat tiles (256 consecutive block pairs per CTA, whatever the width): tiles that start and end inside
 # a block row, many block rows per tile (more than the 32 lanes that issue the bulk copies), rows wider
 # than a tile, a last tile with idle threads.
-FLAT_SHAPES = [(1920, 64, 3), (272, 200, 3), (16, 4104, 1), (4112, 16, 3), (3840, 24, 3), (1040, 72, 1), (304, 136, 4),
-               (32, 2072, 3)]
 
 
 @pytest.mark.parametrize("shape", FLAT_SHAPES)
@@ -541,6 +557,48 @@ def test_host_batch_api_pipelined(ctx, port):
     finally:
         ctx.set_option("host_sub_batch_bytes", 64 << 20)
         ctx.set_option("host_lanes", 3)
+
+
+def test_item_lists_are_an_optimisation_only(port):
+    # the packer reads the item lists of the histogram pass (pieces of <= 2048 items) or rebuilds them from
+    # the planes (denser pieces, or option item_lists = 0): same bytes either way, sparse to dense content
+    import himg_b200
+
+    c = himg_b200.Context(0)
+    try:
+        imgs = np.stack([port.synth(512, 304, 3, 40 + k, 6 + 30 * k) for k in range(3)])
+        for q in (10, 50, 100):
+            out = {}
+            for flag in (1, 0):
+                c.set_option("item_lists", flag)
+                o, s = c.encode_batch(dev(imgs), q, True)
+                out[flag] = (o.cpu().numpy(), s.cpu().numpy())
+            assert np.array_equal(out[0][1], out[1][1])
+            for k in range(3):
+                n = int(out[1][1][k])
+                want = port.encode(imgs[k], q, True)
+                assert n == len(want)
+                assert_same(out[1][0][k, :n], np.frombuffer(want, np.uint8), f"lists on, q{q} image {k}")
+                assert_same(out[0][0][k, :n], out[1][0][k, :n], f"lists off, q{q} image {k}")
+    finally:
+        c.close()
+
+
+def test_decode_broken_segment_chain(ctx, port):
+    # the segment-header walk of a single image runs inside the decode kernel and publishes entries as it
+    # goes: a chain that breaks half way must reject the image (and release every waiting row), never hang
+    img = port.synth(256, 400, 3, 3, 6)
+    good = port.encode(img, 50, True)
+    assert ctx.decode(good) is not None
+    at = good.index(b"FRES") + 8
+    mid = at + (len(good) - at) // 2
+    bad = bytearray(good)
+    bad[mid : mid + 8192] = b"\xff" * min(8192, len(good) - mid)
+    for flags in (0, 1):
+        assert ctx.decode(bytes(bad), flags=flags) is None
+    assert port.decode(bytes(bad)) is None
+    out = ctx.decode(good)
+    assert_same(out, port.decode(good), "decode after a rejected stream")
 
 
 def test_generic_kernels_still_match(port):
