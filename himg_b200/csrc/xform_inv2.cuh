@@ -1,5 +1,6 @@
-// K-inv, one block per thread in int32 with staged planes (v2): the path of 4-channel images; 1- and
-// 3-channel images take the lane-pair kernel of xform_inv3.cuh.  Same arithmetic as k_inverse (xform_kernels.cuh): gather + dequantise +
+// K-inv, one block per thread in int32 with staged planes (v2): the path of 4-channel images and of
+// 1- / 3-channel images whose buffers miss the alignment of the lane-pair kernel (xform_inv4.cuh).
+// Same arithmetic as k_inverse (xform_kernels.cuh): gather + dequantise +
 // inverse WHT with floor >>3 after each pass + low-res add + clamp + inverse colour map
 // (decoder.cpp:366-423).  Differences are structural:
 //
@@ -9,7 +10,7 @@
 //  * 256-thread CTAs whose warps pass the per-channel phases in lock-step (instruction cache);
 //  * per-image dequantisation tables (they travel in-band) live in shared memory.
 //
-// (The row pass sums eight int16 values before its floor shift: 19 bits.  k_inverse3 packs two blocks
+// (The row pass sums eight int16 values before its floor shift: 19 bits.  k_inverse4 packs two blocks
 // per register anyway, guarded by a range vote.)
 //
 // Preconditions (host checked, else k_inverse): width % 128 == 0 or cols % 16 == 0, height % 8 == 0,

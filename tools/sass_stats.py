@@ -2,8 +2,8 @@
 spills, the mnemonics that prove TMA bulk copies / mbarriers / clusters / dp4a / DPX).
 
     python tools/sass_stats.py                 # summary table of every kernel
-    python tools/sass_stats.py k_forward2      # opcode histogram of the kernels whose name matches
-    python tools/sass_stats.py k_forward2 --dump > fwd.sass
+    python tools/sass_stats.py k_forward3      # opcode histogram of the kernels whose name matches
+    python tools/sass_stats.py k_forward3 --dump > fwd.sass
 """
 import collections
 import os
