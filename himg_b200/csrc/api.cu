@@ -506,7 +506,8 @@ int launch_inv4(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, in
   dim3 grid((total_pairs + TP - 1) / TP, 1, n);
   const int smem = NCH * 64 * 2 * TP + kInvTableBytes;
   CK(cudaFuncSetAttribute((k_inverse4<NCH, TP>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  LAUNCH("k_inverse", (k_inverse4<NCH, TP>), grid, TP, smem, d_planes, d_R, g, d_inv, inv_stride, d_pixels, 1u);
+  const uint32_t pr_magic = (uint32_t)((1ull << 32) / (unsigned)(g.cols / 2)) + 1u;  // (cols >= 16 here)
+  LAUNCH("k_inverse", (k_inverse4<NCH, TP>), grid, TP, smem, d_planes, d_R, g, d_inv, inv_stride, d_pixels, 1u, pr_magic);
   return HIMGCU_OK;
 }
 

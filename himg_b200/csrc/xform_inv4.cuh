@@ -259,13 +259,14 @@ __device__ __forceinline__ void inv4_compute(uint8_t *col, const uint8_t *sDq, c
 #pragma unroll
     for (int j4 = 0; j4 < 64; j4 += 4) {
       const uint4 tb = *reinterpret_cast<const uint4 *>(tab + j4);
-      const uint32_t tbj[4] = {tb.x + dq_base, tb.y + dq_base, tb.z + dq_base, tb.w + dq_base};
+      const uint32_t tbj[4] = {tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int j = j4 + k;
         const uint32_t w = *reinterpret_cast<const uint16_t *>(cc + scan_pos(j) * PITCH);
-        const uint32_t a = lds_u16(__dp4a(w, 0x00000002u, tbj[k]));  // table + 2 * code of block A
-        const uint32_t b = lds_u16(__dp4a(w, 0x00000200u, tbj[k]));  // table + 2 * code of block B
+        // (the table base is the uniform part of the load's address: no add per coefficient)
+        const uint32_t a = *reinterpret_cast<const uint16_t *>(sDq + __dp4a(w, 0x00000002u, tbj[k]));  // table + 2 * code of block A
+        const uint32_t b = *reinterpret_cast<const uint16_t *>(sDq + __dp4a(w, 0x00000200u, tbj[k]));  // table + 2 * code of block B
         x[j] = a + (b << 16);
       }
       seen |= (x[j4] | x[j4 + 1]) | (x[j4 + 2] | x[j4 + 3]);  // (two three-input ORs)
@@ -290,10 +291,11 @@ __device__ __forceinline__ void inv4_compute(uint8_t *col, const uint8_t *sDq, c
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) iwht8u(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
-      const uint32_t fixq = pre3 ? 0u : 0x7fff8000u;
       x[0] += 0x7fff8000u;
+      if (!pre3) {
 #pragma unroll
-      for (int q = 1; q < 8; ++q) x[q] += fixq;
+        for (int q = 1; q < 8; ++q) x[q] += 0x7fff8000u;
+      }
 #pragma unroll
       for (int j = 0; j < 64; ++j) x[j] = (x[j] >> 3) & 0x1fff1fffu;
       const uint32_t M = one * 0xf000f000u;  // (opaque to the compiler: stays in a register)
@@ -389,7 +391,8 @@ __device__ __forceinline__ void inv4_compute(uint8_t *col, const uint8_t *sDq, c
 template <int NCH, int TP>
 __global__ void __launch_bounds__(TP, 2)
     k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
-               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels, uint32_t one) {
+               const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels, uint32_t one,
+               uint32_t pr_magic) {
   extern __shared__ __align__(128) uint8_t sPl[];
   constexpr int PITCH = 2 * TP, CPR = TP / 8;  // bytes per tile row, 16-byte chunks per tile row
   static_assert(TP % 32 == 0 && TP == 8 * CPR, "a CTA is 8 groups of one thread per chunk of a tile row");
@@ -405,7 +408,8 @@ __global__ void __launch_bounds__(TP, 2)
   const InvTables *T = reinterpret_cast<const InvTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tab_stride);
   // block row / first pair of the tile's first element: one division per CTA, everything else by
   // carrying (a tile spans few block rows unless the image is very narrow)
-  const int v0 = f0 / PR, p0 = f0 - v0 * PR;
+  // (pr_magic = floor(2^32 / PR) + 1 from the host: the quotient is exact for f0 < 2^32 / PR, i.e. any image)
+  const int v0 = (int)__umulhi((uint32_t)f0, pr_magic), p0 = f0 - v0 * PR;
   auto locate = [&](int k, int &v, int &p) {  // element f0 + k of the image -> block row, pair in the row
     if (PR >= 32) {
       v = v0;

@@ -8,4 +8,5 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "regex:k_forward3|k_inverse4" -c 6 --csv --log-file gpurun_out/${tag}_traffic.csv $B > gpurun_out/${tag}_traffic.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k "regex:k_forward3|k_inverse4" -c 2 -o gpurun_out/${tag}_xform -f python tools/kernel_times.py 512 50 > gpurun_out/${tag}_xform.log 2>&1
 timeout 900 ncu --set full --import-source on --clock-control none -k "regex:k_huff_pack3|k_huff_hist2|k_dec_stream_par|k_lowres_avg" -c 5 -o gpurun_out/${tag}_entropy -f python tools/kernel_times.py 512 50 > gpurun_out/${tag}_entropy.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k "regex:k_dec_stream_par" -c 2 -o gpurun_out/${tag}_dec -f python tools/kernel_times.py 512 50 > gpurun_out/${tag}_dec.log 2>&1
 ls -la gpurun_out | tail -12
