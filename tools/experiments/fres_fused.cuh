@@ -1,3 +1,10 @@
+// EXPERIMENT, NOT BUILT (round 2): measured 9.09 ms per 512 1080p images against 3.97 + 1.98 ms for
+// k_dec_stream_par + k_inverse4, parity green on the whole GPU suite.  Kept for the
+// record.  To rebuild it: include it from csrc/api.cu after xform_inv4.cuh, give inv4_compute a third
+// template parameter GUARD that masks the tile stores (and the int32 redo) of threads with !active, and
+// launch k_fres_fused<3, 240, 128> / <3, 480, 256> / <1, 1024, 512> with grid (rows, n) and
+// fused_smem_bytes<NCH, COLS>() of dynamic shared memory in place of k_dec_stream_fres + stage_inverse.
+//
 // Fused FRES segment decode + inverse transform (the decoder's batch fast path).
 //
 // The reference never stores coefficient planes: DecodeFullResBlockRow (decoder.cpp:331-426) decodes
