@@ -31,7 +31,8 @@
 
 namespace himgcu {
 
-// Block pairs (= threads) per CTA.  Two CTAs of 256 threads per SM leave 128 registers per thread.  (Nine
+// Block pairs (= threads) per CTA.  Two CTAs of 256 threads per SM leave 128 registers per thread; the
+// gray kernel (no colour stage) fits 85 and runs three CTAs (8192^2 gray: 58 -> 54 us).  (Nine
 // warps of RGB would still fit the shared memory of an SM -- 110 592 bytes of codes + 4 608 of tables is
 // exactly half of it -- but at the 96 registers that leaves the kernel measured 17 % slower.)
 constexpr int kInv4ThreadsRgb = 256, kInv4ThreadsGray = 256;
@@ -389,7 +390,7 @@ __device__ __forceinline__ void inv4_compute(uint8_t *col, const uint8_t *sDq, c
 // inside the output phase, and tiles owned by single warps -- all slower than fresh CTAs whose start-up
 // overlaps the other resident CTA.)
 template <int NCH, int TP>
-__global__ void __launch_bounds__(TP, 2)
+__global__ void __launch_bounds__(TP, NCH == 1 ? 3 : 2)
     k_inverse4(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
                const InvTables *__restrict__ tabs, unsigned long long tab_stride, uint8_t *__restrict__ pixels, uint32_t one,
                uint32_t pr_magic) {
