@@ -387,21 +387,32 @@ struct TreeParams {
 };
 
 // grid (n, chunks).  err: set to HIMGCU_ERR_UNSUPPORTED (5) if a code exceeds 32 bits.
+//
+// The construction is a serial chain (n - 1 merges), so what counts is the latency of ONE thread's loop:
+//  * merge: the heads of both queues live in registers (count and node of the next leaf, count and range of
+//    the front group of internal nodes); a pick costs one shared-memory load, a new node three stores;
+//  * codes, depths and the positions of the serialised tree need no stack: a node's index is larger
+//    than its children's, so ONE descending sweep over the internal nodes hands (depth, code, bit position)
+//    down, after an ascending sweep has summed the subtree sizes (leaf = 10 bits, branch = 1 + both);
+//  * the leaves then write their code table entries and their 10 bits of the tree in parallel.
+// (Round 1 walked a stack in shared memory: 65 us for the merge + 35 us for the serialisation of a
+// 261-leaf tree; now about 15 us together.)
 __global__ void __launch_bounds__(kTreeThreads)
     k_huff_tree(const TreeParams P, int *err) {
   __shared__ uint32_t cnt[kMaxNodes];
-  __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
-  __shared__ short lq[kSyms];
-  __shared__ short ist[kSyms], g_start[kSyms], g_top[kSyms];
-  __shared__ uint32_t g_count[kSyms];
+  __shared__ uint32_t kids[kMaxNodes];  // internal node: child a | child b << 16
+  __shared__ short nsym[kSyms];         // leaf node -> symbol
+  __shared__ short lq[kSyms + 1];       // leaves in (count ascending, index DEscending) order
+  __shared__ uint32_t lcnt[kSyms + 1];  // their counts
+  __shared__ short ist[kSyms], gend[kSyms];
+  __shared__ unsigned short bsize[kMaxNodes], bpos[kMaxNodes];
+  __shared__ uint8_t depth[kMaxNodes];
+  __shared__ uint32_t code[kMaxNodes];
   __shared__ uint32_t s_code[kSyms];
   __shared__ uint8_t s_len[kSyms + 3];
   __shared__ uint32_t s_tree[kTreeBytesMax / 4];
   __shared__ uint32_t warp_tot[kTreeThreads / 32 + 1];
-  __shared__ int s_nleaves, s_root, s_bits;
-  __shared__ short st_node[kSyms + 1];
-  __shared__ uint8_t st_bits[kSyms + 1];
-  __shared__ uint32_t st_code[kSyms + 1];
+  __shared__ int s_nleaves, s_bits;
 
   const int t = threadIdx.x;
   const uint32_t *__restrict__ seghist = P.seghist[blockIdx.y];
@@ -435,8 +446,8 @@ __global__ void __launch_bounds__(kTreeThreads)
   const uint32_t li = block_exscan_u32(t < kSyms && my ? 1u : 0u, warp_tot, &total);
   if (t < kSyms && my) {
     cnt[li] = my;
-    ca[li] = cb[li] = -1;
     nsym[li] = (short)t;
+    bsize[li] = 10;  // bit 1 + the 9-bit symbol
   }
   if (t == 0) s_nleaves = (int)total;
   __syncthreads();
@@ -450,91 +461,119 @@ __global__ void __launch_bounds__(kTreeThreads)
       rank += (cj < c || (cj == c && j > t)) ? 1 : 0;
     }
     lq[rank] = (short)t;
+    lcnt[rank] = c;
   }
+  if (t == 0) lq[n] = 0, lcnt[n] = 0;  // (read ahead by the merge, never used)
   __syncthreads();
-  if (t == 0) {
-    // 4. two-queue merge.  Internal nodes are created with non-decreasing counts; equal-count
-    //    internal nodes form groups consumed front group first, NEWEST first inside a group, and
-    //    an internal node beats a leaf of equal count (the reference picks the minimum under
-    //    (count asc, node index desc); huffman_enc.cpp:199-227).
-    int root = 0;
+  if (t == 0 && n > 0) {
+    // 4. two-queue merge.  The reference picks the minimum under (count ascending, node index DEscending)
+    //    (huffman_enc.cpp:199-227).  Internal nodes are created with non-decreasing counts, so they form
+    //    groups of equal count in creation order: the FRONT group is consumed first, newest node first,
+    //    and an internal node beats a leaf of equal count.  While the front group is also the LAST one it
+    //    is a stack that new nodes of the same count are still pushed onto.
+    int root = lq[0];
     if (n > 1) {
-      int ist_n = 0, gfront = 0, glast = -1, lp = 0, next = n;
+      int ist_n = 0, lp = 0, next = n;
+      int fstart = 0, ftop = 0, fend = 0;  // front group [fstart, ftop) of ist, closed end fend (unless it is the last group)
+      uint32_t fcount = 0;
+      bool front_is_last = true;
+      int last_start = 0;
+      uint32_t last_count = 0;
+      uint32_t lc = lcnt[0];
+      int lnode = lq[0];
       for (int merge = 0; merge < n - 1; ++merge) {
         int pick[2];
+        uint32_t pc[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          while (gfront < glast && g_top[gfront] == g_start[gfront]) ++gfront;
-          const bool have_int = glast >= 0 && gfront <= glast &&
-                                (gfront == glast ? ist_n > g_start[glast] : g_top[gfront] > g_start[gfront]);
-          const bool take_int = have_int && (lp >= n || g_count[gfront] <= cnt[lq[lp]]);
-          if (take_int) pick[k] = (gfront == glast) ? ist[--ist_n] : ist[--g_top[gfront]];
-          else pick[k] = lq[lp++];
+          int top = front_is_last ? ist_n : ftop;
+          const bool take_int = top > fstart && (lp >= n || fcount <= lc);
+          if (take_int) {
+            --top;
+            pick[k] = ist[top];
+            pc[k] = fcount;
+            if (front_is_last) {
+              ist_n = top;
+            } else {
+              ftop = top;
+              if (ftop == fstart) {  // exhausted: the next group in creation order
+                fstart = fend;
+                if (fstart == last_start) {
+                  front_is_last = true;
+                  fcount = last_count;
+                } else {
+                  ftop = fend = gend[fstart];
+                  fcount = cnt[ist[fstart]];
+                }
+              }
+            }
+          } else {
+            pick[k] = lnode;
+            pc[k] = lc;
+            ++lp;
+            lc = lcnt[lp];
+            lnode = lq[lp];
+          }
         }
         root = next++;
-        ca[root] = (short)pick[0];
-        cb[root] = (short)pick[1];
-        nsym[root] = -1;
-        const uint32_t c = cnt[pick[0]] + cnt[pick[1]];
+        const uint32_t c = pc[0] + pc[1];
+        kids[root] = (uint32_t)pick[0] | ((uint32_t)pick[1] << 16);
         cnt[root] = c;
-        if (glast >= 0 && ist_n > g_start[glast] && g_count[glast] == c) {
+        if (ist_n > last_start && last_count == c) {
           ist[ist_n++] = (short)root;
-        } else if (glast >= 0 && ist_n == g_start[glast]) {
-          g_count[glast] = c;
+        } else if (ist_n == last_start) {  // the last group is empty: it restarts with this count
+          last_count = c;
+          if (front_is_last) fcount = c;
           ist[ist_n++] = (short)root;
-        } else {
-          if (glast >= 0) g_top[glast] = (short)ist_n;
-          ++glast;
-          g_start[glast] = (short)ist_n;
-          g_count[glast] = c;
+        } else {  // close the last group, open a new one
+          gend[last_start] = (short)ist_n;
+          if (front_is_last) {
+            front_is_last = false;
+            ftop = fend = ist_n;
+          }
+          last_start = ist_n;
+          last_count = c;
           ist[ist_n++] = (short)root;
         }
       }
-    }
-    s_root = root;
-    // 5. pre-order serialisation + code assignment (huffman_enc.cpp:148-180, :229-237)
-    int nbits = 0;
-    if (n > 0) {
-      int sp = 0;
-      st_node[0] = (short)root;
-      st_bits[0] = n == 1 ? 1 : 0;
-      st_code[0] = 0;
-      sp = 1;
-      uint64_t acc = 0;
-      int nacc = 0, wpos = 0;
-      while (sp) {
-        --sp;
-        const int k = st_node[sp];
-        const int bits = st_bits[sp];
-        const uint32_t code = st_code[sp];
-        const int sym = nsym[k];
-        if (sym >= 0) {
-          acc |= (uint64_t)(1u | ((uint32_t)sym << 1)) << nacc;  // bit 1, then the 9-bit symbol
-          nacc += 10;
-          if (bits > 32) atomicMax(err, 5);
-          s_code[sym] = code;
-          s_len[sym] = (uint8_t)bits;
-        } else {
-          nacc += 1;  // bit 0
-          st_node[sp] = cb[k];
-          st_bits[sp] = (uint8_t)min(bits + 1, 255);
-          st_code[sp] = bits < 32 ? code + (1u << bits) : code;
-          ++sp;
-          st_node[sp] = ca[k];
-          st_bits[sp] = (uint8_t)min(bits + 1, 255);
-          st_code[sp] = code;
-          ++sp;
-        }
-        if (nacc >= 32) {
-          s_tree[wpos++] = (uint32_t)acc;
-          acc >>= 32;
-          nacc -= 32;
-        }
+      // 5a. subtree sizes in bits, children before parents
+      for (int k = n; k <= root; ++k) {
+        const uint32_t kd = kids[k];
+        bsize[k] = (unsigned short)(1u + bsize[kd & 0xffffu] + bsize[kd >> 16]);
       }
-      nbits = wpos * 32 + nacc;
-      if (nacc) s_tree[wpos] = (uint32_t)acc;
     }
-    s_bits = nbits;
+    // 5b. depth, code and position of every node, parents before children (pre-order: bit 0, subtree a,
+    //     subtree b; huffman_enc.cpp:148-180, :229-237).  A single leaf gets a 1-bit code.
+    depth[root] = n == 1 ? 1 : 0;
+    code[root] = 0;
+    bpos[root] = 0;
+    for (int k = root; k >= n; --k) {
+      const uint32_t kd = kids[k];
+      const int a = (int)(kd & 0xffffu), b = (int)(kd >> 16);
+      const int d = depth[k];
+      const uint32_t cd = code[k];
+      const unsigned short bp = bpos[k];
+      const uint8_t nd = (uint8_t)min(d + 1, 255);
+      depth[a] = nd;
+      depth[b] = nd;
+      code[a] = cd;
+      code[b] = d < 32 ? cd + (1u << d) : cd;
+      bpos[a] = (unsigned short)(bp + 1);
+      bpos[b] = (unsigned short)(bp + 1 + bsize[a]);
+    }
+    s_bits = bsize[root];
+  }
+  if (t == 0 && n == 0) s_bits = 0;
+  __syncthreads();
+  // 6. every leaf: its entry of the code table, its 10 bits of the serialised tree
+  if (t < n) {
+    const int sym = nsym[t], bits = depth[t];
+    s_code[sym] = code[t];
+    s_len[sym] = (uint8_t)bits;
+    if (bits > 32) atomicMax(err, 5);
+    const uint32_t v = 1u | ((uint32_t)sym << 1), p = bpos[t], sh = p & 31;
+    atomicOr(&s_tree[p >> 5], v << sh);
+    if (sh > 22) atomicOr(&s_tree[(p >> 5) + 1], v >> (32 - sh));
   }
   __syncthreads();
   if (t < kSyms) {
