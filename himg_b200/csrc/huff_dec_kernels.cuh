@@ -193,52 +193,50 @@ __global__ void __launch_bounds__(kDecTreeThreads)
                int lenient, DecTree *__restrict__ trees0, DecTree *__restrict__ trees1, int *__restrict__ status) {
   const ChunkDesc *__restrict__ cd = blockIdx.y ? cd1 : cd0;
   DecTree *__restrict__ trees = blockIdx.y ? trees1 : trees0;
-  __shared__ uint8_t raw[kTreeBytesMax + 8];
+  __shared__ __align__(8) uint8_t raw[kTreeBytesMax + 16];
   __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
   __shared__ uint8_t depth[kMaxNodes];
   __shared__ unsigned short pcode[kMaxNodes];
   __shared__ int s_n, s_ok, s_bits;
-  __shared__ int stk_slot[kMaxNodes + 2];
-  __shared__ uint8_t stk_depth[kMaxNodes + 2];
-  __shared__ unsigned short stk_code[kMaxNodes + 2];
-  __shared__ short anc[kMaxNodes], stk_anc[kMaxNodes + 2];      // ancestor at depth kLutBits (-1: none)
-  __shared__ uint8_t subc[kMaxNodes], stk_sub[kMaxNodes + 2];   // code bits kLutBits .. kLutBits + kSubBits - 1
-  __shared__ short xsub[kMaxNodes];                             // second-level table of a depth-kLutBits node
+  __shared__ unsigned long long stk[kMaxNodes + 2];  // pending RIGHT children: slot | depth | code | ancestor | sub-code
+  __shared__ short anc[kMaxNodes];     // ancestor at depth kLutBits (-1: none)
+  __shared__ uint8_t subc[kMaxNodes];  // code bits kLutBits .. kLutBits + kSubBits - 1
+  __shared__ short xsub[kMaxNodes];    // second-level table of a depth-kLutBits node
   __shared__ int s_nsub;
   const int item = blockIdx.x, t = threadIdx.x;
   DecTree *out = trees + item;
   const ChunkDesc d = cd[item];
   const int avail = d.ok ? (int)min((uint32_t)kTreeBytesMax, d.size) : 0;
-  for (int i = t; i < kTreeBytesMax + 8; i += blockDim.x) raw[i] = i < avail ? data[d.off + i] : 0;
+  for (int i = t; i < kTreeBytesMax + 16; i += blockDim.x) raw[i] = i < avail ? data[d.off + i] : 0;
+  for (int i = t; i < kMaxNodes; i += blockDim.x) ca[i] = cb[i] = nsym[i] = -1;
   for (int i = t; i < kLutSize; i += blockDim.x) out->lut[i] = kLutInvalid;
   __syncthreads();
   if (t == 0) {
+    // Pre-order walk of the serialised tree (leaf = bit 1 + 9-bit symbol, branch = bit 0) by ONE thread:
+    // what counts is the latency of an iteration.  The context of the node about to be read (its slot in
+    // the parent, depth, code so far, ancestor at the LUT depth, sub-code) lives in registers; a branch
+    // pushes the context of its right child as one 64-bit word and goes on with the left child, a leaf
+    // pops; the bits come from a 64-bit register window.  (Round 1 kept five stack arrays and re-read the
+    // bytes bit by bit: 60 us for a 261-leaf tree, now about 10 us.)
     int n = 0, ok = d.ok ? 1 : 0, sp = 0, bit = 0;
     const int nbits = avail * 8;
-    stk_slot[0] = -1;
-    stk_depth[0] = 0;
-    stk_code[0] = 0;
-    stk_anc[0] = -1;
-    stk_sub[0] = 0;
+    const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(raw);
+    unsigned long long buf = (unsigned long long)raw32[0] | ((unsigned long long)raw32[1] << 32);
+    int nb = 64, widx = 2;
+    int slot = -1, dep = 0, my_anc = -1;
+    uint32_t code = 0, my_sub = 0;
     s_nsub = 0;
-    sp = ok ? 1 : 0;
-    while (sp && ok) {
-      --sp;
-      const int slot = stk_slot[sp], dep = stk_depth[sp];
-      const unsigned short code = stk_code[sp];
-      const short my_anc = stk_anc[sp];
-      const uint8_t my_sub = stk_sub[sp];
+    bool more = ok != 0;
+    while (more) {
       if (n >= kMaxNodes) {
         ok = 0;
         break;
       }
       const int k = n++;
-      ca[k] = cb[k] = -1;
-      nsym[k] = -1;
       depth[k] = (uint8_t)dep;
-      pcode[k] = code;
-      anc[k] = my_anc;
-      subc[k] = my_sub;
+      pcode[k] = (unsigned short)code;
+      anc[k] = (short)my_anc;
+      subc[k] = (uint8_t)my_sub;
       if (slot >= 0) {
         if (slot & 1) cb[slot >> 1] = (short)k;
         else ca[slot >> 1] = (short)k;
@@ -247,34 +245,44 @@ __global__ void __launch_bounds__(kDecTreeThreads)
         ok = 0;
         break;
       }
-      const int leaf = (raw[bit >> 3] >> (bit & 7)) & 1;
+      if (nb < 32) {  // (the array is padded with zero words: reading past the tree is harmless)
+        buf |= (unsigned long long)raw32[widx++] << nb;
+        nb += 32;
+      }
+      const int leaf = (int)(buf & 1u);
+      buf >>= 1;
+      --nb;
       ++bit;
       if (leaf) {
         if (bit + 9 > nbits) {
           ok = 0;
           break;
         }
-        int s = 0;
-        for (int q = 0; q < 9; ++q, ++bit) s |= ((raw[bit >> 3] >> (bit & 7)) & 1) << q;
-        nsym[k] = (short)s;
+        nsym[k] = (short)(buf & 511u);
+        buf >>= 9;
+        nb -= 9;
+        bit += 9;
+        if (sp == 0) {
+          more = false;
+        } else {
+          const unsigned long long e = stk[--sp];
+          slot = (int)(e & 0xfffu);
+          dep = (int)((e >> 12) & 0xffu);
+          code = (uint32_t)((e >> 20) & 0xffffu);
+          my_anc = (int)((e >> 36) & 0xfffu) - 1;
+          my_sub = (uint32_t)((e >> 48) & 0xffu);
+        }
       } else {
         const int nd = min(dep + 1, 255);
-        const unsigned short cbit = dep < kLutBits ? (unsigned short)(code | (1u << dep)) : code;
-        const short canc = dep == kLutBits ? (short)k : my_anc;  // children of a depth-kLutBits node start a sub-code
-        const int sb = dep - kLutBits;                           // position of the child's bit inside the sub-code
-        const uint8_t sub1 = (sb >= 0 && sb < kSubBits) ? (uint8_t)(my_sub | (1u << sb)) : my_sub;
-        stk_slot[sp] = k * 2 + 1;
-        stk_depth[sp] = (uint8_t)nd;
-        stk_code[sp] = cbit;
-        stk_anc[sp] = canc;
-        stk_sub[sp] = sub1;
-        ++sp;
-        stk_slot[sp] = k * 2;
-        stk_depth[sp] = (uint8_t)nd;
-        stk_code[sp] = code;
-        stk_anc[sp] = canc;
-        stk_sub[sp] = my_sub;
-        ++sp;
+        const uint32_t cbit = dep < kLutBits ? (code | (1u << dep)) : code;
+        const int canc = dep == kLutBits ? k : my_anc;  // children of a depth-kLutBits node start a sub-code
+        const int sb = dep - kLutBits;                  // position of the child's bit inside the sub-code
+        const uint32_t sub1 = (sb >= 0 && sb < kSubBits) ? (my_sub | (1u << sb)) : my_sub;
+        stk[sp++] = (unsigned long long)(k * 2 + 1) | ((unsigned long long)nd << 12) | ((unsigned long long)cbit << 20) |
+                    ((unsigned long long)(canc + 1) << 36) | ((unsigned long long)sub1 << 48);
+        slot = k * 2;
+        dep = nd;
+        my_anc = canc;
       }
     }
     s_n = n;
