@@ -196,9 +196,10 @@ __global__ void __launch_bounds__(kDecTreeThreads)
   __shared__ __align__(8) uint8_t raw[kTreeBytesMax + 16];
   __shared__ short ca[kMaxNodes], cb[kMaxNodes], nsym[kMaxNodes];
   __shared__ uint8_t depth[kMaxNodes];
-  __shared__ unsigned short pcode[kMaxNodes];
   __shared__ int s_n, s_ok, s_bits;
-  __shared__ unsigned long long stk[kMaxNodes + 2];  // pending RIGHT children: slot | depth | code | ancestor | sub-code
+  __shared__ uint32_t s_lut[kLutSize];   // the single-token LUT is built here (the multi-token LUT reads it back 2048 x ~4 times)
+  __shared__ short stk[kMaxNodes + 2];   // branches whose right child is pending
+  __shared__ short pslot[kMaxNodes];     // 2 * parent + (right child ? 1 : 0); -1 for the root
   __shared__ short anc[kMaxNodes];     // ancestor at depth kLutBits (-1: none)
   __shared__ uint8_t subc[kMaxNodes];  // code bits kLutBits .. kLutBits + kSubBits - 1
   __shared__ short xsub[kMaxNodes];    // second-level table of a depth-kLutBits node
@@ -209,22 +210,18 @@ __global__ void __launch_bounds__(kDecTreeThreads)
   const int avail = d.ok ? (int)min((uint32_t)kTreeBytesMax, d.size) : 0;
   for (int i = t; i < kTreeBytesMax + 16; i += blockDim.x) raw[i] = i < avail ? data[d.off + i] : 0;
   for (int i = t; i < kMaxNodes; i += blockDim.x) ca[i] = cb[i] = nsym[i] = -1;
-  for (int i = t; i < kLutSize; i += blockDim.x) out->lut[i] = kLutInvalid;
   __syncthreads();
   if (t == 0) {
-    // Pre-order walk of the serialised tree (leaf = bit 1 + 9-bit symbol, branch = bit 0) by ONE thread:
-    // what counts is the latency of an iteration.  The context of the node about to be read (its slot in
-    // the parent, depth, code so far, ancestor at the LUT depth, sub-code) lives in registers; a branch
-    // pushes the context of its right child as one 64-bit word and goes on with the left child, a leaf
-    // pops; the bits come from a 64-bit register window.  (Round 1 kept five stack arrays and re-read the
-    // bytes bit by bit: 60 us for a 261-leaf tree, now about 10 us.)
+    // Pre-order walk of the serialised tree (leaf = bit 1 + 9-bit symbol, branch = bit 0) by ONE thread: a
+    // lone thread issues a dependent instruction every few cycles, so the walk only records the STRUCTURE
+    // (symbol, slot in the parent; a branch pushes itself for its right child, a leaf pops), with the bits
+    // in a 64-bit register window.  Depths, codes and LUT ancestors follow in parallel below.
+    // (Round 1 carried all of it through five stack arrays: 60 us for a 261-leaf tree.)
     int n = 0, ok = d.ok ? 1 : 0, sp = 0, bit = 0;
     const int nbits = avail * 8;
     const uint32_t *raw32 = reinterpret_cast<const uint32_t *>(raw);
     unsigned long long buf = (unsigned long long)raw32[0] | ((unsigned long long)raw32[1] << 32);
-    int nb = 64, widx = 2;
-    int slot = -1, dep = 0, my_anc = -1;
-    uint32_t code = 0, my_sub = 0;
+    int nb = 64, widx = 2, slot = -1;
     s_nsub = 0;
     bool more = ok != 0;
     while (more) {
@@ -233,14 +230,7 @@ __global__ void __launch_bounds__(kDecTreeThreads)
         break;
       }
       const int k = n++;
-      depth[k] = (uint8_t)dep;
-      pcode[k] = (unsigned short)code;
-      anc[k] = (short)my_anc;
-      subc[k] = (uint8_t)my_sub;
-      if (slot >= 0) {
-        if (slot & 1) cb[slot >> 1] = (short)k;
-        else ca[slot >> 1] = (short)k;
-      }
+      pslot[k] = (short)slot;
       if (bit + 1 > nbits) {
         ok = 0;
         break;
@@ -262,32 +252,45 @@ __global__ void __launch_bounds__(kDecTreeThreads)
         buf >>= 9;
         nb -= 9;
         bit += 9;
-        if (sp == 0) {
-          more = false;
-        } else {
-          const unsigned long long e = stk[--sp];
-          slot = (int)(e & 0xfffu);
-          dep = (int)((e >> 12) & 0xffu);
-          code = (uint32_t)((e >> 20) & 0xffffu);
-          my_anc = (int)((e >> 36) & 0xfffu) - 1;
-          my_sub = (uint32_t)((e >> 48) & 0xffu);
-        }
+        if (sp == 0) more = false;
+        else slot = stk[--sp];
       } else {
-        const int nd = min(dep + 1, 255);
-        const uint32_t cbit = dep < kLutBits ? (code | (1u << dep)) : code;
-        const int canc = dep == kLutBits ? k : my_anc;  // children of a depth-kLutBits node start a sub-code
-        const int sb = dep - kLutBits;                  // position of the child's bit inside the sub-code
-        const uint32_t sub1 = (sb >= 0 && sb < kSubBits) ? (my_sub | (1u << sb)) : my_sub;
-        stk[sp++] = (unsigned long long)(k * 2 + 1) | ((unsigned long long)nd << 12) | ((unsigned long long)cbit << 20) |
-                    ((unsigned long long)(canc + 1) << 36) | ((unsigned long long)sub1 << 48);
+        stk[sp++] = (short)(k * 2 + 1);
         slot = k * 2;
-        dep = nd;
-        my_anc = canc;
       }
     }
     s_n = n;
     s_ok = ok;
     s_bits = bit;
+  }
+  __syncthreads();
+  // Child links, then depth / code / sub-code / LUT ancestor of every node by a walk UP its parent chain
+  // (a few dozen dependent shared-memory loads per node, all nodes at once, no barrier): the bits of the path
+  // arrive deepest first, so shifting them in from the right leaves bit i of the code = branch taken at depth i.
+  if (s_ok) {
+    const int nn = s_n;
+    for (int k = t; k < nn; k += blockDim.x) {
+      int dlen = 0, cur = k;
+      uint32_t acc = 0;
+      for (int sl = pslot[cur]; sl >= 0; sl = pslot[cur]) {
+        acc = (acc << 1) | (uint32_t)(sl & 1);
+        cur = sl >> 1;
+        ++dlen;
+      }
+      const int sl0 = pslot[k];
+      if (sl0 >= 0) {
+        if (sl0 & 1) cb[sl0 >> 1] = (short)k;
+        else ca[sl0 >> 1] = (short)k;
+      }
+      depth[k] = (uint8_t)min(dlen, 255);
+      subc[k] = (uint8_t)((acc >> kLutBits) & ((1u << kSubBits) - 1u));
+      int a = -1;  // the ancestor at depth kLutBits starts the sub-code of everything below it
+      if (dlen > kLutBits) {
+        a = k;
+        for (int up = dlen - kLutBits; up > 0; --up) a = pslot[a] >> 1;
+      }
+      anc[k] = (short)a;
+    }
   }
   __syncthreads();
   const int n = s_n;
@@ -303,21 +306,32 @@ __global__ void __launch_bounds__(kDecTreeThreads)
     return;
   }
   const bool single = n == 1;
-  for (int k = t; k < n; k += blockDim.x) {
+  for (int k = t; k < n; k += blockDim.x)
     out->nodes[k] = nsym[k] >= 0 ? (0x80000000u | (uint32_t)nsym[k])
                                  : (((uint32_t)ca[k] & 0xffffu) | (((uint32_t)cb[k] & 0xffffu) << 16));
-    const int dep = depth[k];
-    if (nsym[k] >= 0) {
-      if (dep <= kLutBits) {
+  // single-token LUT: every window value walks down from the root (at most kLutBits steps); a leaf on the way
+  // fills the entry, an internal node at depth kLutBits marks a longer code
+  for (int p = t; p < kLutSize; p += blockDim.x) {
+    int node = 0, pos = 0;
+    uint32_t e = kLutInvalid;
+    for (;;) {
+      const int sy = nsym[node];
+      if (sy >= 0) {
         // The reference's decoder consumes ZERO bits per symbol for a single-leaf tree
         // (huffman_dec.cpp:178-188) although its encoder wrote one; lenient mode consumes it.
-        const uint32_t len = (single && lenient) ? 1u : (uint32_t)dep;
-        const uint32_t e = lut_entry(nsym[k], (int)len);
-        for (uint32_t i = 0; i < (1u << (kLutBits - dep)); ++i) out->lut[(i << dep) | pcode[k]] = e;
+        e = lut_entry(sy, (single && lenient) ? 1 : pos);
+        break;
       }
-    } else if (dep == kLutBits) {
-      out->lut[pcode[k]] = kLutLong | (uint32_t)k;
+      if (pos == kLutBits) {
+        e = kLutLong | (uint32_t)node;
+        break;
+      }
+      const int child = ((p >> pos) & 1) ? cb[node] : ca[node];
+      if (child < 0) break;
+      node = child;
+      ++pos;
     }
+    s_lut[p] = e;
   }
   if (t == 0) {
     out->ok = 1;
@@ -347,12 +361,13 @@ __global__ void __launch_bounds__(kDecTreeThreads)
     }
   }
   if (t == 0) out->nsub = min(s_nsub, kSubCap);
-  __syncthreads();  // out->lut and out->sub are complete (written by this CTA)
+  __syncthreads();  // the single-token LUT (shared memory) and out->sub are complete
+  for (int i = t; i < kLutSize; i += blockDim.x) out->lut[i] = s_lut[i];
   for (int p = t; p < kLutSize; p += blockDim.x) {
     int pos = 0, bytes = 0, nlit = 0, tail = 0;
     uint32_t off[2] = {0, 0}, lit[2] = {0, 0}, first = 0;
     while (!single && pos < kLutBits) {
-      const uint32_t e = out->lut[(uint32_t)p >> pos];
+      const uint32_t e = s_lut[(uint32_t)p >> pos];
       if (e & (kLutLong | kLutInvalid)) {
         if (pos == 0) {
           first = kLutInvalid;
