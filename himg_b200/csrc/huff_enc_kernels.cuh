@@ -391,12 +391,13 @@ struct TreeParams {
 // The construction is a serial chain (n - 1 merges), so what counts is the latency of ONE thread's loop:
 //  * merge: the heads of both queues live in registers (count and node of the next leaf, count and range of
 //    the front group of internal nodes); a pick costs one shared-memory load, a new node three stores;
-//  * codes, depths and the positions of the serialised tree need no stack: a node's index is larger
-//    than its children's, so ONE descending sweep over the internal nodes hands (depth, code, bit position)
-//    down, after an ascending sweep has summed the subtree sizes (leaf = 10 bits, branch = 1 + both);
-//  * the leaves then write their code table entries and their 10 bits of the tree in parallel.
+//  * codes, depths and the positions of the serialised tree need no stack and no second serial pass: the
+//    merge records parent links and subtree sizes in bits (leaf = 10, branch = 1 + both), and every LEAF
+//    then walks up its parent chain in parallel: the branch bits arrive deepest first (shifted in from the
+//    right they are the code), the pre-order position is 1 per ancestor + the left sibling subtree wherever
+//    the path turns right; it writes its code table entry and its 10 bits of the tree.
 // (Round 1 walked a stack in shared memory: 65 us for the merge + 35 us for the serialisation of a
-// 261-leaf tree; now about 15 us together.)
+// 261-leaf tree.)
 __global__ void __launch_bounds__(kTreeThreads)
     k_huff_tree(const TreeParams P, int *err) {
   __shared__ uint32_t cnt[kMaxNodes];
@@ -405,9 +406,8 @@ __global__ void __launch_bounds__(kTreeThreads)
   __shared__ short lq[kSyms + 1];       // leaves in (count ascending, index DEscending) order
   __shared__ uint32_t lcnt[kSyms + 1];  // their counts
   __shared__ short ist[kSyms], gend[kSyms];
-  __shared__ unsigned short bsize[kMaxNodes], bpos[kMaxNodes];
-  __shared__ uint8_t depth[kMaxNodes];
-  __shared__ uint32_t code[kMaxNodes];
+  __shared__ unsigned short bsize[kMaxNodes];  // serialised size of the subtree in bits
+  __shared__ short par[kMaxNodes];             // 2 * parent + (second child ? 1 : 0); -1 for the root
   __shared__ uint32_t s_code[kSyms];
   __shared__ uint8_t s_len[kSyms + 3];
   __shared__ uint32_t s_tree[kTreeBytesMax / 4];
@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(kTreeThreads)
         const uint32_t c = pc[0] + pc[1];
         kids[root] = (uint32_t)pick[0] | ((uint32_t)pick[1] << 16);
         cnt[root] = c;
+        par[pick[0]] = (short)(2 * root);
+        par[pick[1]] = (short)(2 * root + 1);
+        bsize[root] = (unsigned short)(1u + bsize[pick[0]] + bsize[pick[1]]);
         if (ist_n > last_start && last_count == c) {
           ist[ist_n++] = (short)root;
         } else if (ist_n == last_start) {  // the last group is empty: it restarts with this count
@@ -536,42 +539,32 @@ __global__ void __launch_bounds__(kTreeThreads)
           ist[ist_n++] = (short)root;
         }
       }
-      // 5a. subtree sizes in bits, children before parents
-      for (int k = n; k <= root; ++k) {
-        const uint32_t kd = kids[k];
-        bsize[k] = (unsigned short)(1u + bsize[kd & 0xffffu] + bsize[kd >> 16]);
-      }
     }
-    // 5b. depth, code and position of every node, parents before children (pre-order: bit 0, subtree a,
-    //     subtree b; huffman_enc.cpp:148-180, :229-237).  A single leaf gets a 1-bit code.
-    depth[root] = n == 1 ? 1 : 0;
-    code[root] = 0;
-    bpos[root] = 0;
-    for (int k = root; k >= n; --k) {
-      const uint32_t kd = kids[k];
-      const int a = (int)(kd & 0xffffu), b = (int)(kd >> 16);
-      const int d = depth[k];
-      const uint32_t cd = code[k];
-      const unsigned short bp = bpos[k];
-      const uint8_t nd = (uint8_t)min(d + 1, 255);
-      depth[a] = nd;
-      depth[b] = nd;
-      code[a] = cd;
-      code[b] = d < 32 ? cd + (1u << d) : cd;
-      bpos[a] = (unsigned short)(bp + 1);
-      bpos[b] = (unsigned short)(bp + 1 + bsize[a]);
-    }
+    par[root] = -1;
     s_bits = bsize[root];
   }
   if (t == 0 && n == 0) s_bits = 0;
   __syncthreads();
-  // 6. every leaf: its entry of the code table, its 10 bits of the serialised tree
+  // 5. every leaf: depth, code and pre-order position by a walk up its parent chain (huffman_enc.cpp:148-180,
+  //    :229-237: bit 0, first subtree, second subtree; the second child's code has bit `depth of the parent`
+  //    set), then its entry of the code table and its 10 bits of the serialised tree.  A single leaf gets a
+  //    1-bit code.
   if (t < n) {
-    const int sym = nsym[t], bits = depth[t];
-    s_code[sym] = code[t];
-    s_len[sym] = (uint8_t)bits;
+    int bits = 0, cur = t;
+    uint32_t cd = 0, p = 0;
+    for (int sl = par[cur]; sl >= 0; sl = par[cur]) {
+      const int up = sl >> 1;
+      cd = (cd << 1) | (uint32_t)(sl & 1);  // (bits beyond 32 fall off: such a tree is refused below)
+      p += 1u + ((sl & 1) ? (uint32_t)bsize[kids[up] & 0xffffu] : 0u);
+      cur = up;
+      ++bits;
+    }
+    if (n == 1) bits = 1;
+    const int sym = nsym[t];
+    s_code[sym] = cd;
+    s_len[sym] = (uint8_t)min(bits, 255);
     if (bits > 32) atomicMax(err, 5);
-    const uint32_t v = 1u | ((uint32_t)sym << 1), p = bpos[t], sh = p & 31;
+    const uint32_t v = 1u | ((uint32_t)sym << 1), sh = p & 31;
     atomicOr(&s_tree[p >> 5], v << sh);
     if (sh > 22) atomicOr(&s_tree[(p >> 5) + 1], v >> (32 - sh));
   }
