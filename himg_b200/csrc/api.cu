@@ -213,7 +213,7 @@ Geom make_geom(int w, int h, int nch, int pstride) {
 }
 
 bool shape_ok(int w, int h, int nch) {
-  if (w < 1 || h < 1 || nch < 1 || nch > 4) return false;
+  if (w < 1 || h < 1 || nch < 1 || nch > 255) return false;  // (the container stores the channel count in one byte)
   const unsigned long long px = (unsigned long long)w * h * nch;
   return px < (1ull << 31) && ((h + 7) >> 3) <= 65535;
 }
@@ -322,11 +322,14 @@ QuantParams make_quant(const EncodeTables &t) {
 
 // ---- stage launchers (device pointers, asynchronous) -------------------------------------------
 
+// cbase / ctotal: the channel group [cbase, cbase + NCH) of an image with ctotal channels (see k_lowres_avg);
+// d_pixels points at the group's first channel.
 template <int NCH>
-int launch_avg(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, bool ycbcr, uint8_t *d_avg) {
+int launch_avg(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g, bool ycbcr, uint8_t *d_avg, int cbase = 0,
+               int ctotal = NCH) {
   dim3 grid((g.cols + kTile - 1) / kTile, g.rows, n);
-  if (ycbcr) LAUNCH("k_lowres_avg", (k_lowres_avg<NCH, true>), grid, kTile, 0, d_pixels, g, d_avg);
-  else LAUNCH("k_lowres_avg", (k_lowres_avg<NCH, false>), grid, kTile, 0, d_pixels, g, d_avg);
+  if (ycbcr) LAUNCH("k_lowres_avg", (k_lowres_avg<NCH, true>), grid, kTile, 0, d_pixels, g, d_avg, cbase, ctotal);
+  else LAUNCH("k_lowres_avg", (k_lowres_avg<NCH, false>), grid, kTile, 0, d_pixels, g, d_avg, cbase, ctotal);
   return HIMGCU_OK;
 }
 
@@ -361,7 +364,11 @@ int stage_lowres(himgcu_ctx *ctx, const uint8_t *d_pixels, int n, const Geom &g,
     case 1: rc = launch_avg<1>(ctx, d_pixels, n, g, false, d_avg); break;
     case 2: rc = launch_avg<2>(ctx, d_pixels, n, g, false, d_avg); break;
     case 3: rc = launch_avg<3>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
-    default: rc = launch_avg<4>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
+    case 4: rc = launch_avg<4>(ctx, d_pixels, n, g, ycbcr, d_avg); break;
+    default:  // more than four channels: the first three, then one launch per further channel
+      rc = launch_avg<3>(ctx, d_pixels, n, g, ycbcr, d_avg, 0, g.nch);
+      for (int c = 3; c < g.nch && !rc; ++c) rc = launch_avg<1>(ctx, d_pixels + c, n, g, false, d_avg, c, g.nch);
+      break;
   }
   if (rc) return rc;
   const int threads = std::min(256, (g.cols + 31) & ~31);
@@ -406,11 +413,11 @@ int stage_lres_encode(himgcu_ctx *ctx, const uint8_t *d_L, int n, const Geom &g,
 
 template <int NCH>
 int launch_fwd(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, int n, const Geom &g, bool ycbcr,
-               const QuantParams &qp, uint8_t *d_planes) {
+               const QuantParams &qp, uint8_t *d_planes, int cbase = 0, int ctotal = NCH) {
   dim3 grid((g.cols + kTile - 1) / kTile, g.rows, n);
   const uint8_t *lut = (const uint8_t *)ctx->full_lut.p;
-  if (ycbcr) LAUNCH("k_forward", (k_forward<NCH, true>), grid, kTile, 0, d_pixels, d_L, g, qp, lut, d_planes);
-  else LAUNCH("k_forward", (k_forward<NCH, false>), grid, kTile, 0, d_pixels, d_L, g, qp, lut, d_planes);
+  if (ycbcr) LAUNCH("k_forward", (k_forward<NCH, true>), grid, kTile, 0, d_pixels, d_L, g, qp, lut, d_planes, cbase, ctotal);
+  else LAUNCH("k_forward", (k_forward<NCH, false>), grid, kTile, 0, d_pixels, d_L, g, qp, lut, d_planes, cbase, ctotal);
   return HIMGCU_OK;
 }
 
@@ -466,15 +473,19 @@ int stage_forward(himgcu_ctx *ctx, const uint8_t *d_pixels, const uint8_t *d_L, 
     case 1: return launch_fwd<1>(ctx, d_pixels, d_L, n, g, false, qp, d_planes);
     case 2: return launch_fwd<2>(ctx, d_pixels, d_L, n, g, false, qp, d_planes);
     case 3: return launch_fwd<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, qp, d_planes);
-    default: return launch_fwd<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, qp, d_planes);
+    case 4: return launch_fwd<4>(ctx, d_pixels, d_L, n, g, t.ycbcr, qp, d_planes);
+    default: break;
   }
+  rc = launch_fwd<3>(ctx, d_pixels, d_L, n, g, t.ycbcr, qp, d_planes, 0, g.nch);
+  for (int c = 3; c < g.nch && !rc; ++c) rc = launch_fwd<1>(ctx, d_pixels + c, d_L, n, g, false, qp, d_planes, c, g.nch);
+  return rc;
 }
 
 template <int NCH>
 int launch_inv(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, int n, const Geom &g,
-               const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels) {
+               const DecTables *d_tabs, unsigned long long tab_stride, uint8_t *d_pixels, int cbase = 0, int ctotal = NCH) {
   dim3 grid((g.cols + kTile - 1) / kTile, g.rows, n);
-  LAUNCH("k_inverse", (k_inverse<NCH>), grid, kTile, 0, d_planes, d_R, g, d_tabs, tab_stride, d_pixels);
+  LAUNCH("k_inverse", (k_inverse<NCH>), grid, kTile, 0, d_planes, d_R, g, d_tabs, tab_stride, d_pixels, cbase, ctotal);
   return HIMGCU_OK;
 }
 
@@ -534,8 +545,12 @@ int stage_inverse(himgcu_ctx *ctx, const uint8_t *d_planes, const uint8_t *d_R, 
     case 1: return launch_inv<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
     case 2: return launch_inv<2>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
     case 3: return launch_inv<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
-    default: return launch_inv<4>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    case 4: return launch_inv<4>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels);
+    default: break;
   }
+  int rc = launch_inv<3>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels, 0, g.nch);
+  for (int c = 3; c < g.nch && !rc; ++c) rc = launch_inv<1>(ctx, d_planes, d_R, n, g, d_tabs, tab_stride, d_pixels, c, g.nch);
+  return rc;
 }
 
 // One Huffman chunk per item, or (image mode) LRES + FRES with the container around them.

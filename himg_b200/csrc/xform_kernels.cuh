@@ -75,9 +75,13 @@ __device__ __forceinline__ int colour_fwd(const Row8<NCH> &r, int i, int c) {
 // the block's top-left corner, clipped to the image (downsampled.cpp:75-94).
 // grid (ceil(cols/kTile), rows, n), block kTile.  avg: [n][nch][rows][cols].
 // ---------------------------------------------------------------------------------------------
+// Channel groups: an image of more than four channels (the reference passes any number through,
+// ycbcr.cpp:24-52, encoder.cpp:69) is handled as its first three channels (colour mapped or not) plus one
+// launch per further channel.  `pixels` then points at the group's first channel (g.pstride = all channels)
+// and cbase / ctotal place the group's planes among the image's: [n][ctotal][rows][cols].
 template <int NCH, bool YCBCR>
 __global__ void __launch_bounds__(kTile) k_lowres_avg(const uint8_t *__restrict__ pixels, Geom g,
-                                                      uint8_t *__restrict__ avg) {
+                                                      uint8_t *__restrict__ avg, int cbase, int ctotal) {
   __shared__ int sB[NCH][kTile + 1];
   const int v = blockIdx.y, t0 = blockIdx.x * kTile, u = t0 + threadIdx.x;
   const uint8_t *img = pixels + (size_t)blockIdx.z * g.img_bytes;
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(kTile) k_lowres_avg(const uint8_t *__restrict_
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int s = A[c] + sB[c][threadIdx.x];
-      avg[(((size_t)blockIdx.z * NCH + c) * g.rows + v) * g.cols + u] = (uint8_t)((s + (cnt >> 1)) / cnt);
+      avg[(((size_t)blockIdx.z * ctotal + cbase + c) * g.rows + v) * g.cols + u] = (uint8_t)((s + (cnt >> 1)) / cnt);
     }
   }
 }
@@ -340,7 +344,7 @@ template <int NCH, bool YCBCR>
 __global__ void __launch_bounds__(kTile)
     k_forward(const uint8_t *__restrict__ pixels, const uint8_t *__restrict__ L, Geom g,
               const __grid_constant__ QuantParams qp, const uint8_t *__restrict__ map_lut,
-              uint8_t *__restrict__ planes) {
+              uint8_t *__restrict__ planes, int cbase, int ctotal) {
   __shared__ uint8_t sLut[7616];
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(map_lut);
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(kTile)
     }
     // ---- subtract the interpolated low-res patch (un-quantised L: SURVEY A.4-5)
     {
-      const LowCorners k = load_corners(L + ((size_t)blockIdx.z * NCH + c) * g.rows * g.cols, g, u, v);
+      const LowCorners k = load_corners(L + ((size_t)blockIdx.z * ctotal + cbase + c) * g.rows * g.cols, g, u, v);
       int lf[9], rt[9];
       nine(k.x11, k.x21, lf);
       nine(k.x12, k.x22, rt);
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(kTile)
     for (int q = 0; q < 8; ++q)
       wht8(x[q], x[8 + q], x[16 + q], x[24 + q], x[32 + q], x[40 + q], x[48 + q], x[56 + q]);
     // ---- sign-magnitude rounding shift, map to 8 bit, scatter in scan order
-    uint8_t *dst = seg + (size_t)c * g.cols * 64 + u;
+    uint8_t *dst = seg + (size_t)(cbase + c) * g.cols * 64 + u;
     const bool chroma = YCBCR && NCH >= 3 && (c == 1 || c == 2);
     if (chroma) {
 #pragma unroll
@@ -439,14 +443,14 @@ template <int NCH>
 __global__ void __launch_bounds__(kTile)
     k_inverse(const uint8_t *__restrict__ planes, const uint8_t *__restrict__ R, Geom g,
               const DecTables *__restrict__ tabs, unsigned long long tab_stride,
-              uint8_t *__restrict__ pixels) {
+              uint8_t *__restrict__ pixels, int cbase, int ctotal) {
   __shared__ int16_t sUn[256];
   __shared__ uint8_t sShift[2][64];
   __shared__ uint32_t sOut[NCH][kTile][17];  // per channel: 64 result bytes per thread (+1 pad)
   const DecTables *T = reinterpret_cast<const DecTables *>(reinterpret_cast<const char *>(tabs) + (size_t)blockIdx.z * tab_stride);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) sUn[i] = T->full_unmap[i];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) sShift[i >> 6][i & 63] = T->shift[i >> 6][i & 63];
-  const bool YCBCR = T->ycbcr != 0;
+  const bool YCBCR = T->ycbcr != 0 && cbase == 0;  // (only the first three channels of an image are colour mapped)
   __syncthreads();
   const int v = blockIdx.y, u = blockIdx.x * kTile + threadIdx.x;
   if (u >= g.cols) return;
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(kTile)
 #pragma unroll 1
   for (int c = 0; c < NCH; ++c) {
     int x[64];
-    const uint8_t *src = seg + (size_t)c * g.cols * 64 + u;
+    const uint8_t *src = seg + (size_t)(cbase + c) * g.cols * 64 + u;
     const uint8_t *sh = sShift[(YCBCR && NCH >= 3 && (c == 1 || c == 2)) ? 1 : 0];
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
@@ -479,7 +483,7 @@ __global__ void __launch_bounds__(kTile)
       for (int i = 0; i < 8; ++i) x[i * 8 + q] >>= 3;
     }
     {
-      const LowCorners k = load_corners(R + ((size_t)blockIdx.z * NCH + c) * g.rows * g.cols, g, u, v);
+      const LowCorners k = load_corners(R + ((size_t)blockIdx.z * ctotal + cbase + c) * g.rows * g.cols, g, u, v);
       int lf[9], rt[9];
       nine(k.x11, k.x21, lf);
       nine(k.x12, k.x22, rt);
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(kTile)
   }
 
   // ---- inverse colour map + interleave + store
-  const bool aligned = bw == 8 && (((size_t)g.w * NCH) & 7) == 0 && ((reinterpret_cast<uintptr_t>(img)) & 7) == 0;
+  const bool aligned = ctotal == NCH && bw == 8 && (((size_t)g.w * NCH) & 7) == 0 && ((reinterpret_cast<uintptr_t>(img)) & 7) == 0;
 #pragma unroll
   for (int y = 0; y < 8; ++y) {
     if (y < bh) {
@@ -525,7 +529,7 @@ __global__ void __launch_bounds__(kTile)
           ow[k >> 2] |= (uint32_t)ch[c] << (8 * (k & 3));
         }
       }
-      uint8_t *p = img + ((size_t)(8 * v + y) * g.w + (size_t)u * 8) * NCH;
+      uint8_t *p = img + ((size_t)(8 * v + y) * g.w + (size_t)u * 8) * ctotal + cbase;
       if (aligned) {
         uint2 *q = reinterpret_cast<uint2 *>(p);
 #pragma unroll
@@ -537,7 +541,7 @@ __global__ void __launch_bounds__(kTile)
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
               const int k = i * NCH + c;
-              p[k] = (uint8_t)(ow[k >> 2] >> (8 * (k & 3)));
+              p[i * ctotal + c] = (uint8_t)(ow[k >> 2] >> (8 * (k & 3)));
             }
       }
     }

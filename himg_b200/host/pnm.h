@@ -58,7 +58,7 @@ inline bool ParseSynthetic(const std::string &spec, Image *img) {
   int w = 0, h = 0, c = 0;
   unsigned seed = 1, amp = 6;
   const int got = std::sscanf(spec.c_str() + 10, "%dx%dx%d:%u:%u", &w, &h, &c, &seed, &amp);
-  if (got < 3 || w < 1 || h < 1 || c < 1 || c > 4) return false;
+  if (got < 3 || w < 1 || h < 1 || c < 1 || c > 255) return false;
   Synthesize(w, h, c, seed, amp, img);
   return true;
 }
@@ -114,7 +114,7 @@ inline bool ReadPnm(const std::string &path, Image *img) {
   } else {
     return false;
   }
-  if (maxval != 255 || img->width < 1 || img->height < 1 || img->channels < 1 || img->channels > 4) return false;
+  if (maxval != 255 || img->width < 1 || img->height < 1 || img->channels < 1 || img->channels > 255) return false;
   img->pixels.resize(static_cast<size_t>(img->width) * img->height * img->channels);
   f.read(reinterpret_cast<char *>(img->pixels.data()), static_cast<std::streamsize>(img->pixels.size()));
   return static_cast<size_t>(f.gcount()) == img->pixels.size();

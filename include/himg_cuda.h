@@ -30,7 +30,7 @@ enum {
   HIMGCU_ERR_ARG = 2,
   HIMGCU_ERR_CUDA = 3,
   HIMGCU_ERR_CAPACITY = 4,    /* output buffer too small */
-  HIMGCU_ERR_UNSUPPORTED = 5  /* e.g. num_channels > 4, Huffman code longer than 32 bits */
+  HIMGCU_ERR_UNSUPPORTED = 5  /* e.g. num_channels > 255, Huffman code longer than 32 bits */
 };
 
 /* decode flags */

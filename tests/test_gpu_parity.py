@@ -601,6 +601,30 @@ def test_decode_broken_segment_chain(ctx, port):
     assert_same(out, port.decode(good), "decode after a rejected stream")
 
 
+@pytest.mark.parametrize("nch", [5, 6, 8])
+def test_more_than_four_channels(ctx, port, nch):
+    # the reference passes any number of channels through (ycbcr.cpp:24-52, encoder.cpp:69): the first three
+    # are colour mapped when asked, the others coded as they are
+    for (w, h) in [(64, 40), (100, 37)]:
+        img = port.synth(w, h, nch, 3, 6)
+        for q, yc in [(50, True), (90, False)]:
+            want = port.encode(img, q, yc)
+            got = ctx.encode(img, q, yc)
+            assert_same(np.frombuffer(got, np.uint8), np.frombuffer(want, np.uint8), f"encode {w}x{h}x{nch} q{q} ycbcr={yc}")
+            px = ctx.decode(want)
+            ref_px = port.decode(want)
+            assert (px is None) == (ref_px is None)
+            if ref_px is None:
+                px, ref_px = ctx.decode(want, flags=1), port.decode(want, strict=False)
+            assert_same(px, ref_px, f"decode {w}x{h}x{nch} q{q} ycbcr={yc}")
+    imgs = np.stack([port.synth(48, 24, nch, 20 + k, 9) for k in range(3)])
+    out, sizes = ctx.encode_batch(dev(imgs), 60, True)
+    for k in range(3):
+        want = port.encode(imgs[k], 60, True)
+        assert int(sizes[k]) == len(want)
+        assert_same(out[k, : len(want)].cpu().numpy(), np.frombuffer(want, np.uint8), f"batch image {k}")
+
+
 def test_generic_kernels_still_match(port):
     """force_generic routes aligned shapes through the generic kernels (k_forward, k_inverse,
     k_huff_hist, k_huff_pack) that normally only see odd shapes; both paths must agree with the
