@@ -57,7 +57,8 @@ def test_encode_bound_and_lres_sizes():
         assert lib.himgcu_lres_size(w, h, n) == lres
         assert lib.himgcu_lres_stride(w, h, n) % 64 == 0 and lib.himgcu_lres_stride(w, h, n) >= lres
         assert lib.himgcu_encode_bound(w, h, n) > w * h * n
-    assert lib.himgcu_encode_bound(0, 10, 3) == 0 and lib.himgcu_encode_bound(10, 10, 5) == 0
+    assert lib.himgcu_encode_bound(0, 10, 3) == 0 and lib.himgcu_encode_bound(10, 10, 256) == 0
+    assert lib.himgcu_encode_bound(10, 10, 5) > 500  # any channel count up to 255, as the reference
 
 
 def test_decode_info_host_only(port):
