@@ -814,8 +814,8 @@ int decode_device(himgcu_ctx *ctx, const uint8_t *d_himg, const unsigned long lo
   ENSURE("planes", (size_t)n * g.planes_bytes, d_planes);
   ENSURE("L", (size_t)n * g.nch * g.rows * g.cols, d_R);
   const unsigned nb = (unsigned)((n + 127) / 128);
-  LAUNCH("k_dec_parse", k_dec_parse, nb, 128, 0, d_himg, d_offsets, d_sizes, n, g.w, g.h, g.nch, d_lcd, d_fcd,
-         d_tabs, d_status);
+  LAUNCH("k_dec_parse", k_dec_parse, (unsigned)((n + 3) / 4), 128, 0, d_himg, d_offsets, d_sizes, n, g.w, g.h, g.nch, d_lcd,
+         d_fcd, d_tabs, d_status);
   LAUNCH("k_dec_tree", k_dec_tree, dim3(n, 2), kDecTreeThreads, 0, d_himg, d_lcd, d_fcd, lenient, d_ltree, d_ftree, d_status);
   // A single image is a chain of latency-bound kernels: its two branches (low-res stream -> DPCM, and
   // segment table -> coefficient planes) share nothing until the inverse transform, so they run on
