@@ -681,9 +681,8 @@ int huff_encode_items(himgcu_ctx *ctx, int n, HuffChunkArgs *chunks, int nchunks
       LAUNCH("k_huff_pack", k_huff_pack3, grid, kTokThreads, 0, chunks[k].d_in, hg, d_trees[k], d_bits[k], d_pos[k],
              d_part[k], d_sizes, d_out, (unsigned long long)out_stride, d_err, lists[k]);
     if (hg.nseg > 1) {
-      const long long tot = (long long)n * hg.nseg;
-      LAUNCH("k_huff_stale", k_huff_stale, (unsigned)((tot + 255) / 256), 256, 0, n, hg.nseg, d_bits[k], d_pos[k],
-             d_sizes, d_out, (unsigned long long)out_stride);
+      LAUNCH("k_huff_stale", k_huff_stale, dim3((hg.nseg + 255) / 256, n), 256, 0, n, hg.nseg, d_bits[k], d_pos[k], d_sizes,
+             d_out, (unsigned long long)out_stride);
     }
   }
   return HIMGCU_OK;

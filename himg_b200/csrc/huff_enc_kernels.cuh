@@ -1127,24 +1127,31 @@ __global__ void __launch_bounds__(kTokThreads, kP3MinCtas)
 
 // ---- K-stale ---------------------------------------------------------------------------------
 // Padding bit p of segment b takes the value WRITTEN at bit p by the most recent earlier segment
-// of the same chunk that is longer than p bits (else 0).  One thread per segment.
-__global__ void k_huff_stale(int n, int nseg, const uint32_t *__restrict__ seg_bits,
-                             const uint32_t *__restrict__ seg_pos, const uint32_t *__restrict__ sizes,
-                             uint8_t *__restrict__ out, unsigned long long out_stride) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)n * nseg) return;
-  const int item = (int)(idx / nseg), b = (int)(idx % nseg);
-  if (b == 0 || sizes[item] == 0) return;
+// of the same chunk that is longer than p bits (else 0).  One thread per segment; the bit lengths of the
+// block's segments and of the 1024 before them sit in shared memory (the walk back over earlier segments
+// was a chain of dependent global loads; it rarely goes further, and then reads global memory again).
+// grid (ceil(nseg / 256), n), block 256.
+constexpr int kStaleWindow = 1024;
+__global__ void __launch_bounds__(256)
+    k_huff_stale(int n, int nseg, const uint32_t *__restrict__ seg_bits, const uint32_t *__restrict__ seg_pos,
+                 const uint32_t *__restrict__ sizes, uint8_t *__restrict__ out, unsigned long long out_stride) {
+  __shared__ uint32_t sb[kStaleWindow + 256];
+  const int item = blockIdx.y, b0 = blockIdx.x * 256, b = b0 + (int)threadIdx.x;
+  if (sizes[item] == 0) return;  // (uniform)
   const uint32_t *bits = seg_bits + (size_t)item * nseg;
   const uint32_t *pos = seg_pos + (size_t)item * nseg;
-  uint32_t lo = bits[b];
+  const int w0 = max(0, b0 - kStaleWindow), w1 = min(nseg, b0 + 256);
+  for (int i = threadIdx.x; i < w1 - w0; i += 256) sb[i] = bits[w0 + i];
+  __syncthreads();
+  if (b == 0 || b >= nseg) return;
+  uint32_t lo = sb[b - w0];
   const uint32_t hi = (lo + 7) & ~7u;  // exclusive end of the padding
   if (lo == hi) return;
   uint8_t *base = out + (size_t)item * out_stride;
   const uint32_t byte_idx = lo >> 3;
   uint32_t add = 0;
   for (int e = b - 1; e >= 0 && lo < hi; --e) {
-    const uint32_t le = bits[e];
+    const uint32_t le = e >= w0 ? sb[e - w0] : bits[e];
     if (le > lo) {
       const uint32_t upto = min(le, hi);  // positions [lo, upto) come from segment e
       const uint32_t mask = ((1u << (upto - (byte_idx << 3))) - 1u) & ~((1u << (lo - (byte_idx << 3))) - 1u);
