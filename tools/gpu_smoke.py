@@ -16,7 +16,7 @@ def main():
     # the last two shapes have a low-res chunk large enough for the multi-CTA packer (parts) and the
     # cluster decoder
     for (w, h, n, q) in [(64, 48, 3, 50), (37, 21, 1, 60), (200, 136, 4, 90), (264, 40, 3, 20), (512, 64, 3, 50), (8192, 16, 1, 100),
-                         (256, 128, 4, 80), (1024, 1024, 3, 50), (2048, 1024, 3, 70)]:
+                         (256, 128, 4, 80), (1024, 1024, 3, 50), (2048, 1024, 3, 70), (72, 40, 6, 50)]:
         img = P.synth(w, h, n, 3, 6)
         got = ctx.encode(img, q, True)
         want = P.encode(img, q, True)
